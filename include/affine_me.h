@@ -1,0 +1,142 @@
+/*
+ * affine_me.h -- C ABI of the B200-native affine motion-estimation search.
+ *
+ * This is the drop-in boundary for the one hot path of iagostorch/VVC-Affine-GPU:
+ * everything the reference host does between "frames are in host memory" and
+ * "per-CU costs / CPMVs are in host memory", i.e. the OpenCL buffer + kernel
+ * dispatch block of /root/reference/main.cpp:484-552 and :746-966 and the
+ * readback of main_aux_functions.h:335-383.  Plain C: pointers and sizes only.
+ *
+ * Reference interface each entry point replaces (file:line under /root/reference):
+ *
+ *   ame_create          clCreateContext / clCreateCommandQueue x5 / clBuildProgram x2 /
+ *                       clCreateKernel x4 / clCreateBuffer (frames, results)
+ *                                                 main.cpp:223-242, 337-359, 373-447, 484-527
+ *   ame_upload_plane    clEnqueueWriteBuffer of a current / reference frame
+ *                                                 main.cpp:572-576, 603, 658, 711-715
+ *                       (the reference-list rotation by clEnqueueCopyBuffer, :597-699,
+ *                        becomes a choice of slot index on the host -- no device copies)
+ *   ame_search          14x clSetKernelArg + clEnqueueNDRangeKernel for FULL_2CP, FULL_3CP,
+ *                       HALF_2CP, HALF_3CP              main.cpp:827-866, 914-953
+ *                       + the two blocking clEnqueueReadBuffer per kernel
+ *                                                 main_aux_functions.h:335-383
+ *   ame_flush/ame_sync  clWaitForEvents / clFinish      main.cpp:856-860, 943-947, 973
+ *   ame_destroy         clRelease*                      main.cpp:1019-1117
+ *   ame_cpmvs           Cpmvs                           typedef.h:1-8
+ *   result indexing     returnArrayIdx                  affine.cl:936, 1929
+ *
+ * Semantics that match the reference: one search = one (current frame,
+ * reference frame, lambda) triple through all four prediction types; results
+ * are four cost arrays (int64) and four CPMV arrays (28-byte structs) indexed
+ * ctu*201 + RETURN_STRIDE_LIST[size] + cu (aligned) and
+ * ctu*284 + HA_RETURN_STRIDE_LIST[group] + cu (half-aligned).
+ *
+ * Threading: one ame_ctx per GPU, driven by one host thread at a time;
+ * contexts share nothing.  All functions return 0 on success or a negative
+ * AME_E_* code; ame_last_error() returns the message of the calling thread's
+ * last failure.  There is no CPU fallback: without a CUDA device ame_create fails.
+ */
+#ifndef AFFINE_ME_H
+#define AFFINE_ME_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AME_API_VERSION 1
+
+enum {
+    AME_OK = 0,
+    AME_E_INVALID = -1,  /* bad argument */
+    AME_E_CUDA = -2,     /* CUDA runtime error (see ame_last_error) */
+    AME_E_NOMEM = -3,
+    AME_E_STATE = -4     /* e.g. too many searches in flight */
+};
+
+/* Prediction types, in the reference's order (constants.h:15-21). */
+enum { AME_FULL_2CP = 0, AME_FULL_3CP = 1, AME_HALF_2CP = 2, AME_HALF_3CP = 3, AME_N_PREDS = 4 };
+
+#define AME_ALIGNED_CUS_PER_CTU 201 /* constants.cl:118 */
+#define AME_HALF_CUS_PER_CTU 284    /* constants.cl:119 */
+
+/* == Cpmvs (typedef.h:5-8): control-point MVs in 1/16-pel units.  nCPs is never
+ * written by the reference kernels; this implementation stores 0 there. */
+typedef struct {
+    int32_t nCPs;
+    int32_t ltx, lty, rtx, rty, lbx, lby;
+} ame_cpmvs;
+
+/* Destination of one search: separate arrays, like the reference's buffers.
+ * cost[p] / cpmvs[p] must hold ame_result_len(ctx, p) elements. */
+typedef struct {
+    int64_t *cost[AME_N_PREDS];
+    ame_cpmvs *cpmvs[AME_N_PREDS];
+} ame_result;
+
+/* Options for ame_set_option. */
+enum {
+    AME_OPT_CVT_RULE = 1,      /* double->int rule of the delta rounding for out-of-range values:
+                                  1 = NVIDIA cvt.rzi (default; what the reference does on an NVIDIA GPU),
+                                  0 = x86 cvttsd2si (what it does on a CPU OpenCL device) */
+    AME_OPT_FUSED_BACKSUB = 2, /* 1 (default) = back-substitution accumulates with FMA, as OpenCL's
+                                  default FP_CONTRACT ON compiles affine.cl:851 */
+    AME_OPT_EARLY_EXIT = 3     /* 1 (default) = stop a CU's refinement once its CPMVs revisit an
+                                  already evaluated state (results are identical either way) */
+};
+
+typedef struct ame_ctx ame_ctx;
+
+/* nCtus = ceil(W/128) * ceil(H/128)  (constants.h:73-79 holds the same numbers as a whitelist). */
+int ame_num_ctus(int width, int height);
+
+/* device: CUDA ordinal.  num_slots: frame planes resident on the GPU (>= 2).
+ * max_in_flight: searches that may be queued before ame_sync (>= 1).
+ * width must be a multiple of 8 and both dimensions >= 16. */
+int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, int max_in_flight);
+void ame_destroy(ame_ctx *ctx);
+
+int ame_result_len(const ame_ctx *ctx, int pred); /* nCtus*201 or nCtus*284 */
+int ame_set_option(ame_ctx *ctx, int option, int value);
+
+/* Asynchronous: copies a W x H plane of 10-bit samples (row-major uint16, like the
+ * reference's `unsigned short` frames) into slot `slot` and builds its
+ * edge-replicated copy used for motion compensation.  `plane` must stay valid
+ * until the next ame_sync; pinned memory makes the copy truly asynchronous. */
+int ame_upload_plane(ame_ctx *ctx, int slot, const uint16_t *plane);
+
+/* Queues one search of the plane in cur_slot against the plane in ref_slot.
+ * `out` arrays are HOST memory and are valid after the next ame_sync.
+ * extra_iters == --ExtraGradientIter. */
+int ame_search(ame_ctx *ctx, int cur_slot, int ref_slot, float lambda, int extra_iters, const ame_result *out);
+
+/* Same search, results left in DEVICE memory (no D2H): `out` arrays are device
+ * pointers obtained from ame_device_result.  Used when the consumer is on the GPU. */
+int ame_search_device(ame_ctx *ctx, int cur_slot, int ref_slot, float lambda, int extra_iters, int result_index);
+int ame_device_result(ame_ctx *ctx, int result_index, ame_result *out); /* result_index < max_in_flight */
+
+/* Launches everything queued so far without waiting. */
+int ame_flush(ame_ctx *ctx);
+/* ame_flush + wait for all queued uploads, searches and result copies. */
+int ame_sync(ame_ctx *ctx);
+
+/* Device time (ms, CUDA events on the context's stream) of the search kernels
+ * launched by the most recent ame_flush/ame_sync, and their launch count. */
+int ame_last_kernel_ms(ame_ctx *ctx, float *ms, int *launches);
+
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
+void *ame_alloc_host(uint64_t bytes);
+void ame_free_host(void *p);
+
+/* CU geometry of result element k (0..200 / 0..283) of prediction type pred:
+ * out = {x, y, w, h} inside the CTU.  Returns the size-group index or -1. */
+int ame_cu_geometry(int pred, int k, int out[4]);
+
+const char *ame_last_error(void);
+int ame_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
