@@ -125,6 +125,12 @@ int ame_sync(ame_ctx *ctx);
  * launched by the most recent ame_flush/ame_sync, and their launch count. */
 int ame_last_kernel_ms(ame_ctx *ctx, float *ms, int *launches);
 
+/* Device-side stopwatch on the context's stream (CUDA events): ame_timer_start records the start event
+ * behind everything issued so far, ame_timer_stop records the stop event, waits for it and returns the
+ * elapsed milliseconds.  Used by bench.py; the events see uploads, kernels and result copies alike. */
+int ame_timer_start(ame_ctx *ctx);
+int ame_timer_stop(ame_ctx *ctx, float *ms);
+
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
 void *ame_alloc_host(uint64_t bytes);
 void ame_free_host(void *p);

@@ -1,0 +1,333 @@
+// C-ABI layer of include/affine_me.h: context, frame slots, queued searches, result copies.
+// Replaces the OpenCL buffer / argument / enqueue / readback code of the reference
+// (/root/reference/main.cpp:484-552, 746-966; main_aux_functions.h:335-383).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "ame_device.h"
+#include "ame_geometry.h"
+
+using namespace ame;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess) return fail(AME_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct Slot {
+    uint16_t *raw = nullptr;  // W x H
+    uint16_t *pad = nullptr;  // (W + 2*kPad) x (H + 2*kPad)
+};
+
+struct ResultBlock {  // one per in-flight search, device memory
+    char *base = nullptr;
+    long long *cost[4];
+    ame_cpmvs *cpmvs[4];
+};
+
+struct Pending {
+    int resultIdx;
+    bool toHost;
+    ame_result host;
+};
+
+struct ame_ctx {
+    int device = 0, W = 0, H = 0, nCtus = 0, ctuCols = 0, padStride = 0;
+    int numSlots = 0, maxInFlight = 0;
+    int cvtRule = 1, fusedBacksub = 1, earlyExit = 1;
+    cudaStream_t stream = nullptr, side = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr, evFork = nullptr, evJoin = nullptr, evT0 = nullptr, evT1 = nullptr;
+    bool timed = false;
+    int lastLaunches = 0;
+    std::vector<Slot> slots;
+    std::vector<ResultBlock> results;
+    PassDesc *dPasses = nullptr;   // device [maxInFlight]
+    PassDesc *hPasses = nullptr;   // pinned [maxInFlight]
+    uint32_t *dBig = nullptr;
+    uint2 *dSmall = nullptr;
+    int nBig = 0, nSmall = 0;
+    std::vector<Pending> queued;   // searches queued since the last flush
+    std::vector<Pending> inflight; // launched, results not yet known complete
+    size_t lens[4];
+};
+
+extern "C" {
+
+int ame_version(void) { return AME_API_VERSION; }
+const char *ame_last_error(void) { return g_err.c_str(); }
+
+int ame_num_ctus(int width, int height) { return ((width + 127) / 128) * ((height + 127) / 128); }
+
+int ame_cu_geometry(int pred, int k, int out[4]) {
+    if (pred < 0 || pred >= AME_N_PREDS || !out) return -1;
+    static const std::vector<CuDesc> tabs[2] = {ctu_cus(0), ctu_cus(1)};
+    const std::vector<CuDesc> &t = tabs[pred >= 2];
+    if (k < 0 || k >= (int)t.size()) return -1;
+    out[0] = t[k].x; out[1] = t[k].y; out[2] = t[k].w; out[3] = t[k].h;
+    return t[k].group;
+}
+
+void *ame_alloc_host(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void ame_free_host(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+void ame_destroy(ame_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (Slot &s : c->slots) { cudaFree(s.raw); cudaFree(s.pad); }
+    for (ResultBlock &r : c->results) cudaFree(r.base);
+    cudaFree(c->dPasses);
+    cudaFree(c->dBig);
+    cudaFree(c->dSmall);
+    if (c->hPasses) cudaFreeHost(c->hPasses);
+    if (c->evStart) cudaEventDestroy(c->evStart);
+    if (c->evStop) cudaEventDestroy(c->evStop);
+    if (c->evT0) cudaEventDestroy(c->evT0);
+    if (c->evT1) cudaEventDestroy(c->evT1);
+    if (c->evFork) cudaEventDestroy(c->evFork);
+    if (c->evJoin) cudaEventDestroy(c->evJoin);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, int max_in_flight) {
+    if (!out) return fail(AME_E_INVALID, "ame_create: out is NULL");
+    *out = nullptr;
+    if (width < 16 || height < 16 || (width % 8) != 0) return fail(AME_E_INVALID, "ame_create: unsupported size %dx%d (width must be a multiple of 8, both >= 16)", width, height);
+    if (num_slots < 2 || max_in_flight < 1) return fail(AME_E_INVALID, "ame_create: need num_slots >= 2 and max_in_flight >= 1");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(AME_E_CUDA, "ame_create: no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(AME_E_INVALID, "ame_create: device %d out of range (%d devices)", device, ndev);
+    CU_TRY(cudaSetDevice(device));
+    ame_ctx *c = new ame_ctx();
+    c->device = device;
+    c->W = width;
+    c->H = height;
+    c->ctuCols = (width + 127) / 128;
+    c->nCtus = ame_num_ctus(width, height);
+    c->padStride = width + 2 * kPad;
+    c->numSlots = num_slots;
+    c->maxInFlight = max_in_flight;
+    for (int p = 0; p < 4; p++) c->lens[p] = (size_t)c->nCtus * (p < 2 ? AME_ALIGNED_CUS_PER_CTU : AME_HALF_CUS_PER_CTU);
+#define CTX_TRY(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            int rc_ = fail(e_ == cudaErrorMemoryAllocation ? AME_E_NOMEM : AME_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+            ame_destroy(c);                                                                    \
+            return rc_;                                                                        \
+        }                                                                                      \
+    } while (0)
+    CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CTX_TRY(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    CTX_TRY(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+    CTX_TRY(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
+    CTX_TRY(cudaEventCreate(&c->evT0));
+    CTX_TRY(cudaEventCreate(&c->evT1));
+    CTX_TRY(cudaEventCreate(&c->evStart));
+    CTX_TRY(cudaEventCreate(&c->evStop));
+    c->slots.resize(num_slots);
+    const size_t rawBytes = (size_t)width * height * sizeof(uint16_t);
+    const size_t padBytes = (size_t)c->padStride * (height + 2 * kPad) * sizeof(uint16_t) + 64;
+    for (Slot &s : c->slots) {
+        CTX_TRY(cudaMalloc(&s.raw, rawBytes));
+        CTX_TRY(cudaMalloc(&s.pad, padBytes));
+    }
+    size_t off[8], total = 0;
+    for (int p = 0; p < 4; p++) { off[p] = total; total += (c->lens[p] * sizeof(long long) + 255) & ~(size_t)255; }
+    for (int p = 0; p < 4; p++) { off[4 + p] = total; total += (c->lens[p] * sizeof(ame_cpmvs) + 255) & ~(size_t)255; }
+    c->results.resize(max_in_flight);
+    for (ResultBlock &r : c->results) {
+        CTX_TRY(cudaMalloc(&r.base, total));
+        for (int p = 0; p < 4; p++) {
+            r.cost[p] = reinterpret_cast<long long *>(r.base + off[p]);
+            r.cpmvs[p] = reinterpret_cast<ame_cpmvs *>(r.base + off[4 + p]);
+        }
+    }
+    CTX_TRY(cudaMalloc(&c->dPasses, sizeof(PassDesc) * max_in_flight));
+    CTX_TRY(cudaHostAlloc(&c->hPasses, sizeof(PassDesc) * max_in_flight, cudaHostAllocDefault));
+    const CtuSchedule sched = build_schedule();
+    c->nBig = (int)sched.big.size();
+    c->nSmall = (int)sched.small.size();
+    CTX_TRY(cudaMalloc(&c->dBig, sizeof(uint32_t) * c->nBig));
+    CTX_TRY(cudaMalloc(&c->dSmall, sizeof(uint2) * c->nSmall));
+    CTX_TRY(cudaMemcpy(c->dBig, sched.big.data(), sizeof(uint32_t) * c->nBig, cudaMemcpyHostToDevice));
+    static_assert(sizeof(SmallTask) == sizeof(uint2), "SmallTask layout");
+    CTX_TRY(cudaMemcpy(c->dSmall, sched.small.data(), sizeof(uint2) * c->nSmall, cudaMemcpyHostToDevice));
+#undef CTX_TRY
+    *out = c;
+    return AME_OK;
+}
+
+int ame_result_len(const ame_ctx *c, int pred) {
+    if (!c || pred < 0 || pred >= AME_N_PREDS) return fail(AME_E_INVALID, "ame_result_len: bad argument");
+    return (int)c->lens[pred];
+}
+
+int ame_set_option(ame_ctx *c, int option, int value) {
+    if (!c) return fail(AME_E_INVALID, "ame_set_option: ctx is NULL");
+    switch (option) {
+        case AME_OPT_CVT_RULE: c->cvtRule = value ? 1 : 0; return AME_OK;
+        case AME_OPT_FUSED_BACKSUB: c->fusedBacksub = value ? 1 : 0; return AME_OK;
+        case AME_OPT_EARLY_EXIT: c->earlyExit = value ? 1 : 0; return AME_OK;
+    }
+    return fail(AME_E_INVALID, "ame_set_option: unknown option %d", option);
+}
+
+int ame_upload_plane(ame_ctx *c, int slot, const uint16_t *plane) {
+    if (!c || !plane) return fail(AME_E_INVALID, "ame_upload_plane: NULL argument");
+    if (slot < 0 || slot >= c->numSlots) return fail(AME_E_INVALID, "ame_upload_plane: slot %d out of range", slot);
+    CU_TRY(cudaSetDevice(c->device));
+    // Searches queued against the old contents of this slot must be launched first (stream order then
+    // keeps them ahead of the overwrite).
+    if (!c->queued.empty()) { int rc = ame_flush(c); if (rc) return rc; }
+    Slot &s = c->slots[slot];
+    CU_TRY(cudaMemcpyAsync(s.raw, plane, (size_t)c->W * c->H * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+    launch_pad(s.raw, s.pad, c->W, c->H, c->padStride, c->stream);
+    CU_TRY(cudaGetLastError());
+    return AME_OK;
+}
+
+static int queue_search(ame_ctx *c, int cur_slot, int ref_slot, float lambda, int extra_iters, bool toHost, const ame_result *out, int resultIdx) {
+    if (cur_slot < 0 || cur_slot >= c->numSlots || ref_slot < 0 || ref_slot >= c->numSlots) return fail(AME_E_INVALID, "ame_search: slot out of range");
+    if (extra_iters < 0 || extra_iters > 64) return fail(AME_E_INVALID, "ame_search: extra_iters %d out of range", extra_iters);
+    if ((int)(c->queued.size() + c->inflight.size()) >= c->maxInFlight) return fail(AME_E_STATE, "ame_search: %d searches already in flight; call ame_sync", c->maxInFlight);
+    if (resultIdx < 0) {
+        // first result block not used by a queued / in-flight search
+        std::vector<char> used(c->maxInFlight, 0);
+        for (const Pending &p : c->queued) used[p.resultIdx] = 1;
+        for (const Pending &p : c->inflight) used[p.resultIdx] = 1;
+        for (int i = 0; i < c->maxInFlight && resultIdx < 0; i++) if (!used[i]) resultIdx = i;
+    } else {
+        if (resultIdx >= c->maxInFlight) return fail(AME_E_INVALID, "ame_search_device: result_index out of range");
+        for (const Pending &p : c->queued) if (p.resultIdx == resultIdx) return fail(AME_E_STATE, "ame_search_device: result block %d busy", resultIdx);
+        for (const Pending &p : c->inflight) if (p.resultIdx == resultIdx) return fail(AME_E_STATE, "ame_search_device: result block %d busy", resultIdx);
+    }
+    Pending pn;
+    pn.resultIdx = resultIdx;
+    pn.toHost = toHost;
+    if (toHost) pn.host = *out;
+    PassDesc &d = c->hPasses[c->inflight.size() + c->queued.size()];  // slot stays untouched until ame_sync
+    d.cur = c->slots[cur_slot].raw;
+    d.refPad = c->slots[ref_slot].pad;
+    for (int p = 0; p < 4; p++) { d.cost[p] = c->results[resultIdx].cost[p]; d.cpmvs[p] = c->results[resultIdx].cpmvs[p]; }
+    d.lambda = lambda;
+    d.extraIter = extra_iters;
+    c->queued.push_back(pn);
+    return AME_OK;
+}
+
+int ame_search(ame_ctx *c, int cur_slot, int ref_slot, float lambda, int extra_iters, const ame_result *out) {
+    if (!c || !out) return fail(AME_E_INVALID, "ame_search: NULL argument");
+    for (int p = 0; p < 4; p++) if (!out->cost[p] || !out->cpmvs[p]) return fail(AME_E_INVALID, "ame_search: result array %d is NULL", p);
+    return queue_search(c, cur_slot, ref_slot, lambda, extra_iters, true, out, -1);
+}
+
+int ame_search_device(ame_ctx *c, int cur_slot, int ref_slot, float lambda, int extra_iters, int result_index) {
+    if (!c) return fail(AME_E_INVALID, "ame_search_device: ctx is NULL");
+    if (result_index < 0) return fail(AME_E_INVALID, "ame_search_device: result_index out of range");
+    return queue_search(c, cur_slot, ref_slot, lambda, extra_iters, false, nullptr, result_index);
+}
+
+int ame_device_result(ame_ctx *c, int result_index, ame_result *out) {
+    if (!c || !out || result_index < 0 || result_index >= c->maxInFlight) return fail(AME_E_INVALID, "ame_device_result: bad argument");
+    for (int p = 0; p < 4; p++) { out->cost[p] = (int64_t *)c->results[result_index].cost[p]; out->cpmvs[p] = c->results[result_index].cpmvs[p]; }
+    return AME_OK;
+}
+
+int ame_flush(ame_ctx *c) {
+    if (!c) return fail(AME_E_INVALID, "ame_flush: ctx is NULL");
+    if (c->queued.empty()) return AME_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    const int n = (int)c->queued.size();
+    // Descriptor slots [inflight, inflight + n) are not reused before ame_sync, so the copy can be async.
+    const size_t first = c->inflight.size();
+    CU_TRY(cudaMemcpyAsync(c->dPasses + first, c->hPasses + first, sizeof(PassDesc) * n, cudaMemcpyHostToDevice, c->stream));
+    KParams kp;
+    kp.W = c->W; kp.H = c->H; kp.ctuCols = c->ctuCols; kp.nCtus = c->nCtus; kp.padStride = c->padStride;
+    kp.nPasses = n;
+    kp.cvtRule = c->cvtRule; kp.fusedBacksub = c->fusedBacksub; kp.earlyExit = c->earlyExit;
+    kp.passes = c->dPasses + first;
+    kp.bigTab = c->dBig; kp.smallTab = c->dSmall; kp.nBig = c->nBig; kp.nSmall = c->nSmall;
+    CU_TRY(cudaEventRecord(c->evStart, c->stream));
+    c->lastLaunches = launch_search(kp, c->stream, c->side, c->evFork, c->evJoin);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(c->evStop, c->stream));
+    c->timed = true;
+    for (const Pending &p : c->queued) {
+        if (p.toHost) {
+            const ResultBlock &r = c->results[p.resultIdx];
+            for (int k = 0; k < 4; k++) {
+                CU_TRY(cudaMemcpyAsync(p.host.cost[k], r.cost[k], c->lens[k] * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+                CU_TRY(cudaMemcpyAsync(p.host.cpmvs[k], r.cpmvs[k], c->lens[k] * sizeof(ame_cpmvs), cudaMemcpyDeviceToHost, c->stream));
+            }
+        }
+        c->inflight.push_back(p);
+    }
+    c->queued.clear();
+    return AME_OK;
+}
+
+int ame_sync(ame_ctx *c) {
+    if (!c) return fail(AME_E_INVALID, "ame_sync: ctx is NULL");
+    int rc = ame_flush(c);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    c->inflight.clear();
+    return AME_OK;
+}
+
+int ame_last_kernel_ms(ame_ctx *c, float *ms, int *launches) {
+    if (!c || !ms) return fail(AME_E_INVALID, "ame_last_kernel_ms: NULL argument");
+    if (!c->timed) return fail(AME_E_STATE, "ame_last_kernel_ms: nothing launched yet");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaEventSynchronize(c->evStop));
+    CU_TRY(cudaEventElapsedTime(ms, c->evStart, c->evStop));
+    if (launches) *launches = c->lastLaunches;
+    return AME_OK;
+}
+
+int ame_timer_start(ame_ctx *c) {
+    if (!c) return fail(AME_E_INVALID, "ame_timer_start: ctx is NULL");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaEventRecord(c->evT0, c->stream));
+    return AME_OK;
+}
+
+int ame_timer_stop(ame_ctx *c, float *ms) {
+    if (!c || !ms) return fail(AME_E_INVALID, "ame_timer_stop: NULL argument");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaEventRecord(c->evT1, c->stream));
+    CU_TRY(cudaEventSynchronize(c->evT1));
+    CU_TRY(cudaEventElapsedTime(ms, c->evT0, c->evT1));
+    return AME_OK;
+}
+
+}  // extern "C"

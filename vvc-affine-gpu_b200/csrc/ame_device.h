@@ -1,0 +1,42 @@
+// Internal interface between the C-ABI layer (ame_api.cu) and the kernels
+// (ame_kernels.cu).  Not installed; the public boundary is include/affine_me.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/affine_me.h"
+
+namespace ame {
+
+// Edge replication margin of the motion-compensation copy of a plane.  clipMv
+// keeps CU origin + MV inside [-135, W+7] (aux_functions.cl:51-67); a sub-block
+// sits up to 124 px further and the filter reaches 3/4 px beyond it, so 144 is
+// the worst case; 160 keeps rows 64-byte aligned.
+constexpr int kPad = 160;
+
+// One queued search, as the kernels see it.
+struct PassDesc {
+    const uint16_t *cur;     // raw current plane, stride = W
+    const uint16_t *refPad;  // padded reference plane, stride = padStride, (0,0) of the frame at [kPad][kPad]
+    long long *cost[4];
+    ame_cpmvs *cpmvs[4];
+    float lambda;
+    int extraIter;
+};
+
+struct KParams {
+    int W, H, ctuCols, nCtus, padStride;
+    int nPasses;
+    int cvtRule, fusedBacksub, earlyExit;
+    const PassDesc *passes;   // device array [nPasses]
+    const uint32_t *bigTab;   // device array [nBig] packed CU words
+    const uint2 *smallTab;    // device array [nSmall] (first, second) packed CU words
+    int nBig, nSmall;
+};
+
+// Launches the search kernels for all passes on `stream`; returns launches made.
+int launch_search(const KParams &kp, cudaStream_t stream, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);
+// dst (padded, stride padStride) <- edge-replicated src (W x H).
+void launch_pad(const uint16_t *src, uint16_t *dst, int W, int H, int padStride, cudaStream_t stream);
+
+}  // namespace ame
