@@ -164,8 +164,12 @@ def test_solver_known_systems():
         M[1:n + 1, :n] = A
         M[1:n + 1, n] = A @ x
         assert np.allclose(ob.solve(M, n), x, atol=1e-9)
-        M0 = np.zeros((7, 7))  # all-zero system -> NaN propagates (0/0), caller maps NaN to a zero delta
-        assert np.isnan(ob.solve(M0, n)).all()
+        M0 = np.zeros((7, 7))  # all-zero system: NaNs appear below row 1 but the zero test on M[1][0] resets the result
+        assert (ob.solve(M0, n) == 0).all()
+        M1 = np.zeros((7, 7))  # rank 1 (e.g. a horizontal ramp): the first zero-pivot row stays finite, so the same test fires
+        M1[1, 0] = 100.0
+        M1[1, n] = 50.0
+        assert (ob.solve(M1, n) == 0).all()
 
 
 def test_geometry_tables():
