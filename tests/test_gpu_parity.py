@@ -1,0 +1,225 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against
+  * the golden fixtures (outputs of the unmodified reference run through NVIDIA OpenCL on a B200),
+  * the CPU oracle on fresh seeded inputs,
+  * size-independent properties at the full 1080p size.
+Bit-exact everywhere: costs (int64) and all six CPMV components of every logged CU."""
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import ame_logs
+import oracle_binding as ob
+import synth_frames as sf
+from conftest import load_pkg
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+FLD = ("LTx", "LTy", "RTx", "RTy", "LBx", "LBy")
+
+
+def _diff(costs_a, cp_a, costs_b, cp_b):
+    bad = 0
+    for p in range(4):
+        m = np.asarray(costs_a[p]) != np.asarray(costs_b[p])
+        for f in FLD:
+            m |= cp_a[p][f] != cp_b[p][f]
+        bad += int(m.sum())
+    return bad
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    p = load_pkg()
+    p.lib()
+    return p
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_cuda_matches_reference_logs(pkg, path):
+    d = np.load(path)
+    orig, recon, qp, extra = d["orig"], d["recon"], int(d["qp"]), int(d["extra_iter"])
+    n, H, W = orig.shape
+    lists = ob.ref_lists(n)
+    ctx = pkg.AffineME(W, H)
+    try:
+        for k, (poc, r) in enumerate(ame_logs.pass_list(n)):
+            costs, cp = ctx.ref_pass(recon[lists[poc - 1][r]], orig[poc - 1], ob.lambda_for(qp, poc), extra)
+            gold_c = [d["cost_%d_%d" % (k, p)] for p in range(4)]
+            gold_m = [d["cpmv_%d_%d" % (k, p)] for p in range(4)]
+            assert _diff(costs, cp, gold_c, gold_m) == 0, (path, poc, r)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("W,H,seed,qp", [(416, 240, 11, 27), (416, 240, 12, 37), (832, 480, 13, 32), (1280, 720, 14, 22)])
+def test_cuda_matches_oracle_on_seeded_inputs(pkg, W, H, seed, qp):
+    orig, recon = sf.sequences(1, W, H, qp, seed=sf.SEED + seed)
+    lam = ob.lambda_for(qp, 1)
+    ctx = pkg.AffineME(W, H)
+    try:
+        costs, cp = ctx.ref_pass(recon[0], orig[0], lam)
+    finally:
+        ctx.close()
+    oc, om = ob.ref_pass(recon[0], orig[0], lam)
+    assert _diff(costs, cp, oc, om) == 0
+
+
+def test_options_match_oracle_options(pkg):
+    """Both FP switches and the extra-iteration count are honoured identically on degenerate content."""
+    rng = np.random.default_rng(21)
+    W, H = 416, 240
+    cur = np.where(rng.random((H, W)) < 0.5, 0, 1023).astype(np.uint16)       # saturated noise
+    ref = np.roll(cur, 3, axis=1)
+    ref[:, ::7] = 512
+    lam = ob.lambda_for(32, 1)
+    for fused in (0, 1):
+        for cvt in (0, 1):
+            ctx = pkg.AffineME(W, H)
+            try:
+                ctx.set_option(pkg.OPT_FUSED_BACKSUB, fused)
+                ctx.set_option(pkg.OPT_CVT_RULE, cvt)
+                costs, cp = ctx.ref_pass(ref, cur, lam, 1)
+            finally:
+                ctx.close()
+            oc, om = ob.ref_pass(ref, cur, lam, ob.default_opts(extra_iter=1, fused_backsub=fused, cvt_rule=cvt))
+            assert _diff(costs, cp, oc, om) == 0, (fused, cvt)
+
+
+def test_early_exit_is_exact(pkg):
+    """Stopping at a revisited CPMV state must not change any decision."""
+    orig, recon = sf.sequences(2, 832, 480, 32, seed=sf.SEED + 31)
+    lam = ob.lambda_for(32, 2)
+    out = []
+    for ee in (1, 0):
+        ctx = pkg.AffineME(832, 480)
+        try:
+            ctx.set_option(pkg.OPT_EARLY_EXIT, ee)
+            out.append(ctx.ref_pass(recon[0], orig[1], lam))
+        finally:
+            ctx.close()
+    assert _diff(out[0][0], out[0][1], out[1][0], out[1][1]) == 0
+
+
+def test_1080p_properties(pkg):
+    """Full-size checks: batched == one-by-one, run-to-run determinism, the fixed rows of out-of-frame CUs, and
+    CTU row 0 against the oracle run on a 1920x256 strip (row 0's searches never reach the strip's bottom edge,
+    so the strip and the full frame give the same decisions there)."""
+    W, H = 1920, 1080
+    orig, recon = sf.sequences(2, W, H, 32)
+    lists = ob.ref_lists(2)
+    passes = [(1, 0), (2, 0), (2, 1)]
+    ctx = pkg.AffineME(W, H, num_slots=4, max_in_flight=4)
+    try:
+        single = []
+        for (poc, r) in passes:
+            single.append(ctx.ref_pass(recon[lists[poc - 1][r]], orig[poc - 1], ob.lambda_for(32, poc)))
+        # batched: all planes resident, three searches in one launch
+        res = [pkg.HostResult(ctx) for _ in passes]
+        ctx.upload(0, orig[0]); ctx.upload(1, orig[1]); ctx.upload(2, recon[0]); ctx.upload(3, recon[1])
+        for k, (poc, r) in enumerate(passes):
+            ctx.search(poc - 1, 2 + lists[poc - 1][r], ob.lambda_for(32, poc), res[k])
+        ctx.sync()
+        for k in range(3):
+            assert _diff(res[k].cost, res[k].cpmvs, single[k][0], single[k][1]) == 0
+        # determinism
+        again = ctx.ref_pass(recon[0], orig[0], ob.lambda_for(32, 1))
+        assert _diff(again[0], again[1], single[0][0], single[0][1]) == 0
+        # out-of-frame CUs of the bottom CTU row: 1080p / QP32 / POC1 -> 473 (2-CP), 631 (3-CP), zero CPMVs
+        costs, cp = single[0]
+        for pred in range(4):
+            per = 201 if pred < 2 else 284
+            c = costs[pred].reshape(135, per)
+            geo = [pkg.cu_geometry(pred, k)[1] for k in range(per)]
+            outside = np.array([g[1] + g[3] > 1080 - 8 * 128 for g in geo])
+            if pred % 2 == 1:
+                # 3-CP starts from LB = clipMv(0): zero only while the CU origin is at most 7 rows below the picture
+                outside &= np.array([1024 + g[1] <= 1080 + 7 for g in geo])
+            want = 473 if pred % 2 == 0 else 631
+            assert (c[120:, outside] == want).all()
+            m = cp[pred].reshape(135, per)[120:, outside]
+            assert all((m[f] == 0).all() for f in FLD)
+        for r in res:
+            r.free()
+    finally:
+        ctx.close()
+    # oracle on the first CTU row of the same pass (15 CTUs, a 1920x128 strip is not equivalent because of the
+    # bottom picture edge) -> compare the full-frame oracle for CTU row 0 only on a 1920x256 strip where row 0's
+    # searches (MVs within +-8 px here) never reach the strip's bottom edge.
+    strip = 256
+    oc, om = ob.ref_pass(recon[0][:strip], orig[0][:strip], ob.lambda_for(32, 1))
+    for pred in range(4):
+        per = 201 if pred < 2 else 284
+        a = single[0][0][pred].reshape(135, per)[:15]
+        b = oc[pred].reshape(30, per)[:15]
+        assert (a == b).all()
+
+
+def test_error_behaviour(pkg):
+    ctx = pkg.AffineME(416, 240, num_slots=2, max_in_flight=1)
+    try:
+        with pytest.raises(pkg.AmeError):
+            ctx.upload(5, np.zeros((240, 416), np.uint16))
+        res = pkg.HostResult(ctx)
+        ctx.upload(0, np.zeros((240, 416), np.uint16)); ctx.upload(1, np.zeros((240, 416), np.uint16))
+        ctx.search(0, 1, 10.0, res)
+        with pytest.raises(pkg.AmeError, match="in flight"):
+            ctx.search(0, 1, 10.0, res)
+        ctx.sync()
+        assert int(res.cost[0][0]) == int(np.floor(np.float32(10.0) * np.float32(6)))  # zero residual, minimum rate
+        res.free()
+    finally:
+        ctx.close()
+    with pytest.raises(pkg.AmeError):
+        pkg.AffineME(417, 240)
+
+
+def _expected_log_bytes(d, W, H, pred, name):
+    """Re-creates one log file of the reference from the golden arrays (format main_aux_functions.h:439, 518)."""
+    n = d["orig"].shape[0]
+    nct = ame_logs.num_ctus(W, H)
+    cols = (W + 127) // 128
+    st, total = ame_logs.strides(pred)
+    lines = [ame_logs.HEADER]
+    for k, (poc, r) in enumerate(ame_logs.pass_list(n)):
+        c, m = d["cost_%d_%d" % (k, pred)], d["cpmv_%d_%d" % (k, pred)]
+        for g, (w, h, cnt) in enumerate(ame_logs.groups(pred)):
+            if "%dx%d" % (w, h) != name:
+                continue
+            for ctu in range(nct):
+                for i in range(cnt):
+                    _, (x, y, _, _) = ob.cu_geometry(1 if pred >= 2 else 0, st[g] + i)
+                    j = ctu * total + st[g] + i
+                    lines.append("%d,0,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d" % (
+                        poc, r, ctu, i, x + (ctu % cols) * 128, y + (ctu // cols) * 128, c[j], m["LTx"][j], m["LTy"][j],
+                        m["RTx"][j], m["RTy"][j], m["LBx"][j], m["LBy"][j]))
+    return ("\n".join(lines) + "\n").encode()
+
+
+def test_cli_logs_are_byte_identical_to_the_reference(pkg, tmp_path):
+    """The drop-in CLI on the CSV inputs of a golden run writes the same 40 log files, byte for byte."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "affine_416x240_f3_q32.npz"))
+    n, H, W = d["orig"].shape
+    sf.write_csv(str(tmp_path / "orig.csv"), d["orig"])
+    sf.write_csv(str(tmp_path / "recon.csv"), d["recon"])
+    for extra_args in ([], ["--BatchFrames", "1"]):
+        prefix = str(tmp_path / ("log%d" % len(extra_args)))
+        r = subprocess.run([pkg.CLI_PATH, "-f", str(n), "-s", "%dx%d" % (W, H), "-q", "32", "-o", str(tmp_path / "orig.csv"),
+                            "-r", str(tmp_path / "recon.csv"), "-l", prefix] + extra_args, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "START HOST @" in r.stdout and "FINISH HOST @" in r.stdout and "TOTAL_EXEC_TIME(3x)," in r.stdout
+        assert "POC   2  RefIdx  1  -> lambda 70.335617" in r.stdout
+        files = ame_logs.log_files(prefix)
+        assert len(files) == 40
+        for pred in range(4):
+            names = []
+            for (w, h, _) in ame_logs.groups(pred):
+                if "%dx%d" % (w, h) not in names:
+                    names.append("%dx%d" % (w, h))
+            for nm in names:
+                got = open(prefix + ame_logs.PRED_TAGS[pred] + nm + ".csv", "rb").read()
+                assert got == _expected_log_bytes(d, W, H, pred, nm), (pred, nm)
