@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libaffine_me.so")
+LIB_PATH = os.environ.get("AME_LIB") or os.path.join(HERE, "libaffine_me.so")  # AME_LIB: development A/B builds
 CLI_PATH = os.path.join(HERE, "bin", "affine_b200")
 
 PRED_NAMES = ("FULL_2CP", "FULL_3CP", "HALF_2CP", "HALF_3CP")
