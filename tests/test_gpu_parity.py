@@ -69,6 +69,25 @@ def test_cuda_matches_oracle_on_seeded_inputs(pkg, W, H, seed, qp):
     assert _diff(costs, cp, oc, om) == 0
 
 
+@pytest.mark.parametrize("W,H", [(3840, 2160), (7680, 4320)])
+def test_large_frames_match_oracle(pkg, W, H):
+    """BASELINE.json configs[2]/[3]: 4K and 8K frames (8K is outside the reference's size whitelist,
+    constants.h:73-79; the oracle runs the same kernels' arithmetic with nCtus = ceil(W/128)*ceil(H/128))."""
+    tile = sf.sequences(1, 960, 544, 32, seed=sf.SEED + 41)          # tiled to full size: cheap to generate
+    reps = (H + 543) // 544, (W + 959) // 960
+    cur = np.tile(tile[0][0], reps)[:H, :W].copy()
+    ref = np.tile(tile[1][0], reps)[:H, :W].copy()
+    ref[::37, ::41] ^= 5                                             # break the exact tiling periodicity
+    lam = ob.lambda_for(32, 1)
+    ctx = pkg.AffineME(W, H, num_slots=2, max_in_flight=1)
+    try:
+        costs, cp = ctx.ref_pass(ref, cur, lam)
+    finally:
+        ctx.close()
+    oc, om = ob.ref_pass(ref, cur, lam)
+    assert _diff(costs, cp, oc, om) == 0
+
+
 def test_options_match_oracle_options(pkg):
     """Both FP switches and the extra-iteration count are honoured identically on degenerate content."""
     rng = np.random.default_rng(21)
