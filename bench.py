@@ -238,8 +238,8 @@ def run_b200(args, rank, world, local_rank):
 
     def upload_all(qp):
         for f in range(N_FRAMES):
-            ctx.upload(f, pin_orig.array[f])
-            ctx.upload(N_FRAMES + f, pin_recon[qp].array[f])
+            ctx.upload(f, pin_orig.array[f], pkg.ROLE_CURRENT)
+            ctx.upload(N_FRAMES + f, pin_recon[qp].array[f], pkg.ROLE_REFERENCE)
 
     def queue_all(qp, to_host):
         for k, (poc, r, refpoc) in enumerate(passes):

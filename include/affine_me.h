@@ -101,10 +101,17 @@ int ame_result_len(const ame_ctx *ctx, int pred); /* nCtus*201 or nCtus*284 */
 int ame_set_option(ame_ctx *ctx, int option, int value);
 
 /* Asynchronous: copies a W x H plane of 10-bit samples (row-major uint16, like the
- * reference's `unsigned short` frames) into slot `slot` and builds its
- * edge-replicated copy used for motion compensation.  `plane` must stay valid
+ * reference's `unsigned short` frames) into slot `slot` and prepares it for motion compensation
+ * (edge replication + first interpolation stage).  `plane` must stay valid
  * until the next ame_sync; pinned memory makes the copy truly asynchronous. */
 int ame_upload_plane(ame_ctx *ctx, int slot, const uint16_t *plane);
+
+/* Same with an explicit role mask.  AME_ROLE_CURRENT: the plane will be searched FOR (original frames);
+ * AME_ROLE_REFERENCE: the plane will be searched IN (reconstructed frames) -- this runs the horizontal
+ * interpolation stage for all 16 phases once and keeps the result (16 x (W+320) x (H+320) x 4 bytes of device
+ * memory, allocated on the slot's first reference upload).  ame_upload_plane gives both roles. */
+enum { AME_ROLE_CURRENT = 1, AME_ROLE_REFERENCE = 2 };
+int ame_upload_plane_ex(ame_ctx *ctx, int slot, const uint16_t *plane, int roles);
 
 /* Queues one search of the plane in cur_slot against the plane in ref_slot.
  * `out` arrays are HOST memory and are valid after the next ame_sync.

@@ -18,9 +18,10 @@ PRED_NAMES = ("FULL_2CP", "FULL_3CP", "HALF_2CP", "HALF_3CP")
 CPMV_DTYPE = np.dtype([("nCPs", "<i4"), ("LTx", "<i4"), ("LTy", "<i4"), ("RTx", "<i4"),
                        ("RTy", "<i4"), ("LBx", "<i4"), ("LBy", "<i4")])
 OPT_CVT_RULE, OPT_FUSED_BACKSUB, OPT_EARLY_EXIT = 1, 2, 3
+ROLE_CURRENT, ROLE_REFERENCE = 1, 2
 
 # every symbol include/affine_me.h declares
-EXPORTS = ("ame_num_ctus", "ame_create", "ame_destroy", "ame_result_len", "ame_set_option", "ame_upload_plane",
+EXPORTS = ("ame_num_ctus", "ame_create", "ame_destroy", "ame_result_len", "ame_set_option", "ame_upload_plane", "ame_upload_plane_ex",
            "ame_search", "ame_search_device", "ame_device_result", "ame_flush", "ame_sync", "ame_last_kernel_ms",
            "ame_timer_start", "ame_timer_stop", "ame_alloc_host", "ame_free_host", "ame_cu_geometry", "ame_last_error", "ame_version")
 
@@ -48,6 +49,7 @@ def lib():
         L.ame_result_len.argtypes = [C.c_void_p, C.c_int]
         L.ame_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.ame_upload_plane.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ame_upload_plane_ex.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.ame_search.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.POINTER(AmeResult)]
         L.ame_search_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int]
         L.ame_device_result.argtypes = [C.c_void_p, C.c_int, C.POINTER(AmeResult)]
@@ -150,12 +152,12 @@ class AffineME:
     def set_option(self, opt, value):
         _check(lib().ame_set_option(self.h, opt, value))
 
-    def upload(self, slot, plane):
+    def upload(self, slot, plane, roles=ROLE_CURRENT | ROLE_REFERENCE):
         """plane: (H, W) uint16 numpy array or PinnedArray; kept alive until sync()."""
         arr = plane.array if isinstance(plane, PinnedArray) else np.ascontiguousarray(plane, dtype=np.uint16)
         assert arr.shape == (self.H, self.W), arr.shape
         self._keep.append(arr)
-        _check(lib().ame_upload_plane(self.h, slot, arr.ctypes.data))
+        _check(lib().ame_upload_plane_ex(self.h, slot, arr.ctypes.data, roles))
 
     def search(self, cur_slot, ref_slot, lam, result, extra_iters=0):
         _check(lib().ame_search(self.h, cur_slot, ref_slot, C.c_float(lam), extra_iters, C.byref(result.c)))
@@ -187,8 +189,8 @@ class AffineME:
         """Convenience: one search on two host planes -> (costs[4], cpmvs[4]) numpy copies."""
         res = HostResult(self)
         try:
-            self.upload(0, cur)
-            self.upload(1, ref)
+            self.upload(0, cur, ROLE_CURRENT)
+            self.upload(1, ref, ROLE_REFERENCE)
             self.search(0, 1, lam, res, extra_iters)
             self.sync()
             return [c.copy() for c in res.cost], [m.copy() for m in res.cpmvs]

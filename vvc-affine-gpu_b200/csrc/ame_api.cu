@@ -33,8 +33,9 @@ static int fail(int code, const char *fmt, ...) {
     } while (0)
 
 struct Slot {
-    uint16_t *raw = nullptr;  // W x H
-    uint16_t *pad = nullptr;  // (W + 2*kPad) x (H + 2*kPad)
+    uint16_t *raw = nullptr;    // W x H, current-frame role
+    uint32_t *phase = nullptr;  // 16 pre-filtered phase planes, reference role; allocated on first use
+    bool hasRef = false;        // phase planes match the current contents of raw
 };
 
 struct ResultBlock {  // one per in-flight search, device memory
@@ -57,6 +58,8 @@ struct ame_ctx {
     cudaEvent_t evStart = nullptr, evStop = nullptr, evFork = nullptr, evJoin = nullptr, evT0 = nullptr, evT1 = nullptr;
     bool timed = false;
     int lastLaunches = 0;
+    uint16_t *padScratch = nullptr;  // (W + 2*kPad) x (H + 2*kPad) edge-replicated plane, input of the phase filter
+    size_t planeElems = 0;
     std::vector<Slot> slots;
     std::vector<ResultBlock> results;
     PassDesc *dPasses = nullptr;   // device [maxInFlight]
@@ -98,7 +101,8 @@ void ame_destroy(ame_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (Slot &s : c->slots) { cudaFree(s.raw); cudaFree(s.pad); }
+    for (Slot &s : c->slots) { cudaFree(s.raw); cudaFree(s.phase); }
+    cudaFree(c->padScratch);
     for (ResultBlock &r : c->results) cudaFree(r.base);
     cudaFree(c->dPasses);
     cudaFree(c->dBig);
@@ -154,11 +158,9 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
     CTX_TRY(cudaEventCreate(&c->evStop));
     c->slots.resize(num_slots);
     const size_t rawBytes = (size_t)width * height * sizeof(uint16_t);
-    const size_t padBytes = (size_t)c->padStride * (height + 2 * kPad) * sizeof(uint16_t) + 64;
-    for (Slot &s : c->slots) {
-        CTX_TRY(cudaMalloc(&s.raw, rawBytes));
-        CTX_TRY(cudaMalloc(&s.pad, padBytes));
-    }
+    c->planeElems = (size_t)c->padStride * (height + 2 * kPad);
+    CTX_TRY(cudaMalloc(&c->padScratch, c->planeElems * sizeof(uint16_t) + 64));
+    for (Slot &s : c->slots) CTX_TRY(cudaMalloc(&s.raw, rawBytes));
     size_t off[8], total = 0;
     for (int p = 0; p < 4; p++) { off[p] = total; total += (c->lens[p] * sizeof(long long) + 255) & ~(size_t)255; }
     for (int p = 0; p < 4; p++) { off[4 + p] = total; total += (c->lens[p] * sizeof(ame_cpmvs) + 255) & ~(size_t)255; }
@@ -200,23 +202,38 @@ int ame_set_option(ame_ctx *c, int option, int value) {
     return fail(AME_E_INVALID, "ame_set_option: unknown option %d", option);
 }
 
-int ame_upload_plane(ame_ctx *c, int slot, const uint16_t *plane) {
+int ame_upload_plane_ex(ame_ctx *c, int slot, const uint16_t *plane, int roles) {
     if (!c || !plane) return fail(AME_E_INVALID, "ame_upload_plane: NULL argument");
     if (slot < 0 || slot >= c->numSlots) return fail(AME_E_INVALID, "ame_upload_plane: slot %d out of range", slot);
+    if (!(roles & (AME_ROLE_CURRENT | AME_ROLE_REFERENCE))) return fail(AME_E_INVALID, "ame_upload_plane: no role given");
     CU_TRY(cudaSetDevice(c->device));
     // Searches queued against the old contents of this slot must be launched first (stream order then
     // keeps them ahead of the overwrite).
     if (!c->queued.empty()) { int rc = ame_flush(c); if (rc) return rc; }
     Slot &s = c->slots[slot];
     CU_TRY(cudaMemcpyAsync(s.raw, plane, (size_t)c->W * c->H * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
-    launch_pad(s.raw, s.pad, c->W, c->H, c->padStride, c->stream);
-    CU_TRY(cudaGetLastError());
+    s.hasRef = false;
+    if (roles & AME_ROLE_REFERENCE) {
+        if (!s.phase) {
+            cudaError_t e = cudaMalloc(&s.phase, 16 * c->planeElems * sizeof(uint32_t));
+            if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? AME_E_NOMEM : AME_E_CUDA, "phase planes of slot %d: %s", slot, cudaGetErrorString(e));
+        }
+        launch_pad(s.raw, c->padScratch, c->W, c->H, c->padStride, c->stream);
+        launch_phase_planes(c->padScratch, s.phase, c->W, c->H, c->padStride, c->stream);
+        CU_TRY(cudaGetLastError());
+        s.hasRef = true;
+    }
     return AME_OK;
+}
+
+int ame_upload_plane(ame_ctx *c, int slot, const uint16_t *plane) {
+    return ame_upload_plane_ex(c, slot, plane, AME_ROLE_CURRENT | AME_ROLE_REFERENCE);
 }
 
 static int queue_search(ame_ctx *c, int cur_slot, int ref_slot, float lambda, int extra_iters, bool toHost, const ame_result *out, int resultIdx) {
     if (cur_slot < 0 || cur_slot >= c->numSlots || ref_slot < 0 || ref_slot >= c->numSlots) return fail(AME_E_INVALID, "ame_search: slot out of range");
     if (extra_iters < 0 || extra_iters > 64) return fail(AME_E_INVALID, "ame_search: extra_iters %d out of range", extra_iters);
+    if (!c->slots[ref_slot].hasRef) return fail(AME_E_STATE, "ame_search: slot %d was not uploaded with the reference role", ref_slot);
     if ((int)(c->queued.size() + c->inflight.size()) >= c->maxInFlight) return fail(AME_E_STATE, "ame_search: %d searches already in flight; call ame_sync", c->maxInFlight);
     if (resultIdx < 0) {
         // first result block not used by a queued / in-flight search
@@ -235,7 +252,7 @@ static int queue_search(ame_ctx *c, int cur_slot, int ref_slot, float lambda, in
     if (toHost) pn.host = *out;
     PassDesc &d = c->hPasses[c->inflight.size() + c->queued.size()];  // slot stays untouched until ame_sync
     d.cur = c->slots[cur_slot].raw;
-    d.refPad = c->slots[ref_slot].pad;
+    d.refPhase = c->slots[ref_slot].phase;
     for (int p = 0; p < 4; p++) { d.cost[p] = c->results[resultIdx].cost[p]; d.cpmvs[p] = c->results[resultIdx].cpmvs[p]; }
     d.lambda = lambda;
     d.extraIter = extra_iters;
@@ -271,6 +288,7 @@ int ame_flush(ame_ctx *c) {
     CU_TRY(cudaMemcpyAsync(c->dPasses + first, c->hPasses + first, sizeof(PassDesc) * n, cudaMemcpyHostToDevice, c->stream));
     KParams kp;
     kp.W = c->W; kp.H = c->H; kp.ctuCols = c->ctuCols; kp.nCtus = c->nCtus; kp.padStride = c->padStride;
+    kp.planeElems = c->planeElems;
     kp.nPasses = n;
     kp.cvtRule = c->cvtRule; kp.fusedBacksub = c->fusedBacksub; kp.earlyExit = c->earlyExit;
     kp.passes = c->dPasses + first;

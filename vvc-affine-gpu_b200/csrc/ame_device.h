@@ -17,7 +17,8 @@ constexpr int kPad = 160;
 // One queued search, as the kernels see it.
 struct PassDesc {
     const uint16_t *cur;     // raw current plane, stride = W
-    const uint16_t *refPad;  // padded reference plane, stride = padStride, (0,0) of the frame at [kPad][kPad]
+    const uint32_t *refPhase;  // 16 pre-filtered phase planes of the reference (launch_phase_planes), each padStride x
+                               // (H + 2*kPad) pair words, (0,0) of the frame at [kPad][kPad]
     long long *cost[4];
     ame_cpmvs *cpmvs[4];
     float lambda;
@@ -26,6 +27,7 @@ struct PassDesc {
 
 struct KParams {
     int W, H, ctuCols, nCtus, padStride;
+    size_t planeElems;  // padStride * (H + 2*kPad): words per phase plane
     int nPasses;
     int cvtRule, fusedBacksub, earlyExit;
     const PassDesc *passes;   // device array [nPasses]
@@ -38,5 +40,7 @@ struct KParams {
 int launch_search(const KParams &kp, cudaStream_t stream, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);
 // dst (padded, stride padStride) <- edge-replicated src (W x H).
 void launch_pad(const uint16_t *src, uint16_t *dst, int W, int H, int padStride, cudaStream_t stream);
+// phase[16][H + 2*kPad][padStride] <- first interpolation stage of the padded plane `pad`, all 16 phases.
+void launch_phase_planes(const uint16_t *pad, uint32_t *phase, int W, int H, int padStride, cudaStream_t stream);
 
 }  // namespace ame

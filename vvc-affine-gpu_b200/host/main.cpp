@@ -167,12 +167,12 @@ int main(int argc, char **argv) {
             std::map<int, int> refSlot;
             for (int i = 0; ok && i < bt.nFrames; i++) {
                 const int f = bt.firstFrame + i;
-                ok = ok && ame_upload_plane(ctx, i, orig + plane * f) == AME_OK;
+                ok = ok && ame_upload_plane_ex(ctx, i, orig + plane * f, AME_ROLE_CURRENT) == AME_OK;
                 for (int rp : lists[f]) {
                     if (refSlot.count(rp)) continue;
                     const int s = B + (int)refSlot.size();
                     refSlot[rp] = s;
-                    ok = ok && ame_upload_plane(ctx, s, recon + plane * rp) == AME_OK;
+                    ok = ok && ame_upload_plane_ex(ctx, s, recon + plane * rp, AME_ROLE_REFERENCE) == AME_OK;
                 }
             }
             for (size_t k = 0; ok && k < bt.ids.size(); k++) {
