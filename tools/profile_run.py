@@ -39,4 +39,14 @@ for rep in range(a.reps):
     ms = ctx.timer_stop()
     ctx.sync()
     print("rep %d: %d passes in %.3f ms -> %.1f passes/s" % (rep, len(passes), ms, 1000.0 * len(passes) / ms), flush=True)
+import ctypes
+st = (ctypes.c_ulonglong * 24)()
+if hasattr(pkg.lib(), "ame_debug_stats"):
+    pkg.lib().ame_debug_stats(st, 0)
+    v = list(st)
+    if sum(v):
+        tot = a.reps
+        print("2-CP searches by states evaluated:", [x // tot for x in v[0:8]])
+        print("3-CP searches by states evaluated:", [x // tot for x in v[8:16]])
+        print("exit: fixed point %d, 2-cycle %d, 3-cycle %d, iteration limit %d" % tuple(x // tot for x in v[16:20]))
 ctx.close()

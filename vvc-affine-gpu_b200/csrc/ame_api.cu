@@ -348,4 +348,10 @@ int ame_timer_stop(ame_ctx *c, float *ms) {
     return AME_OK;
 }
 
+/* Not part of the public header: development counters (see ame_kernels.cu, -DAME_STATS). */
+int ame_debug_stats(unsigned long long *out24, int reset) {
+    debug_stats(out24, reset != 0);
+    return AME_OK;
+}
+
 }  // extern "C"

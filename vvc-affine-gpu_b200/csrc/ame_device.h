@@ -43,4 +43,7 @@ void launch_pad(const uint16_t *src, uint16_t *dst, int W, int H, int padStride,
 // phase[16][H + 2*kPad][padStride] <- first interpolation stage of the padded plane `pad`, all 16 phases.
 void launch_phase_planes(const uint16_t *pad, uint32_t *phase, int W, int H, int padStride, cudaStream_t stream);
 
+// Development counters of builds with -DAME_STATS (zeros otherwise).
+void debug_stats(unsigned long long *out24, bool reset);
+
 }  // namespace ame
