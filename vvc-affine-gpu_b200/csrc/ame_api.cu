@@ -45,7 +45,7 @@ struct ResultBlock {  // one per in-flight search, device memory
 };
 
 struct Pending {
-    int resultIdx;
+    int resultIdx, curSlot, refSlot;
     bool toHost;
     ame_result host;
 };
@@ -54,7 +54,10 @@ struct ame_ctx {
     int device = 0, W = 0, H = 0, nCtus = 0, ctuCols = 0, padStride = 0;
     int numSlots = 0, maxInFlight = 0;
     int cvtRule = 1, fusedBacksub = 1, earlyExit = 1;
-    cudaStream_t stream = nullptr, side = nullptr;
+    cudaStream_t stream = nullptr, side = nullptr;  // search kernels (big CUs / small CUs)
+    cudaStream_t up = nullptr, down = nullptr;      // plane uploads + preparation / result copies
+    cudaEvent_t evUp = nullptr, evKernels = nullptr, evAux = nullptr;
+    bool kernelsRecorded = false;
     cudaEvent_t evStart = nullptr, evStop = nullptr, evFork = nullptr, evJoin = nullptr, evT0 = nullptr, evT1 = nullptr;
     bool timed = false;
     int lastLaunches = 0;
@@ -100,7 +103,7 @@ void ame_free_host(void *p) {
 void ame_destroy(ame_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (cudaStream_t s : {c->up, c->stream, c->side, c->down}) if (s) cudaStreamSynchronize(s);
     for (Slot &s : c->slots) { cudaFree(s.raw); cudaFree(s.phase); }
     cudaFree(c->padScratch);
     for (ResultBlock &r : c->results) cudaFree(r.base);
@@ -114,6 +117,9 @@ void ame_destroy(ame_ctx *c) {
     if (c->evT1) cudaEventDestroy(c->evT1);
     if (c->evFork) cudaEventDestroy(c->evFork);
     if (c->evJoin) cudaEventDestroy(c->evJoin);
+    for (cudaEvent_t e : {c->evUp, c->evKernels, c->evAux}) if (e) cudaEventDestroy(e);
+    if (c->up) cudaStreamDestroy(c->up);
+    if (c->down) cudaStreamDestroy(c->down);
     if (c->side) cudaStreamDestroy(c->side);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -150,6 +156,11 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
     } while (0)
     CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CTX_TRY(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    CTX_TRY(cudaStreamCreateWithFlags(&c->up, cudaStreamNonBlocking));
+    CTX_TRY(cudaStreamCreateWithFlags(&c->down, cudaStreamNonBlocking));
+    CTX_TRY(cudaEventCreateWithFlags(&c->evUp, cudaEventDisableTiming));
+    CTX_TRY(cudaEventCreateWithFlags(&c->evKernels, cudaEventDisableTiming));
+    CTX_TRY(cudaEventCreateWithFlags(&c->evAux, cudaEventDisableTiming));
     CTX_TRY(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
     CTX_TRY(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
     CTX_TRY(cudaEventCreate(&c->evT0));
@@ -207,22 +218,28 @@ int ame_upload_plane_ex(ame_ctx *c, int slot, const uint16_t *plane, int roles) 
     if (slot < 0 || slot >= c->numSlots) return fail(AME_E_INVALID, "ame_upload_plane: slot %d out of range", slot);
     if (!(roles & (AME_ROLE_CURRENT | AME_ROLE_REFERENCE))) return fail(AME_E_INVALID, "ame_upload_plane: no role given");
     CU_TRY(cudaSetDevice(c->device));
-    // Searches queued against the old contents of this slot must be launched first (stream order then
-    // keeps them ahead of the overwrite).
-    if (!c->queued.empty()) { int rc = ame_flush(c); if (rc) return rc; }
+    // Uploads run on their own stream so that they overlap the search kernels of earlier batches.  A slot that
+    // queued searches still refer to is launched first; a slot that launched searches may still be reading makes
+    // the upload stream wait for those kernels.
+    bool queuedUse = false, inflightUse = false;
+    for (const Pending &p : c->queued) queuedUse |= (p.curSlot == slot || p.refSlot == slot);
+    if (queuedUse) { int rc = ame_flush(c); if (rc) return rc; }
+    for (const Pending &p : c->inflight) inflightUse |= (p.curSlot == slot || p.refSlot == slot);
+    if (inflightUse && c->kernelsRecorded) CU_TRY(cudaStreamWaitEvent(c->up, c->evKernels, 0));
     Slot &s = c->slots[slot];
-    CU_TRY(cudaMemcpyAsync(s.raw, plane, (size_t)c->W * c->H * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(s.raw, plane, (size_t)c->W * c->H * sizeof(uint16_t), cudaMemcpyHostToDevice, c->up));
     s.hasRef = false;
     if (roles & AME_ROLE_REFERENCE) {
         if (!s.phase) {
             cudaError_t e = cudaMalloc(&s.phase, 16 * c->planeElems * sizeof(uint32_t));
             if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? AME_E_NOMEM : AME_E_CUDA, "phase planes of slot %d: %s", slot, cudaGetErrorString(e));
         }
-        launch_pad(s.raw, c->padScratch, c->W, c->H, c->padStride, c->stream);
-        launch_phase_planes(c->padScratch, s.phase, c->W, c->H, c->padStride, c->stream);
+        launch_pad(s.raw, c->padScratch, c->W, c->H, c->padStride, c->up);
+        launch_phase_planes(c->padScratch, s.phase, c->W, c->H, c->padStride, c->up);
         CU_TRY(cudaGetLastError());
         s.hasRef = true;
     }
+    CU_TRY(cudaEventRecord(c->evUp, c->up));
     return AME_OK;
 }
 
@@ -248,6 +265,8 @@ static int queue_search(ame_ctx *c, int cur_slot, int ref_slot, float lambda, in
     }
     Pending pn;
     pn.resultIdx = resultIdx;
+    pn.curSlot = cur_slot;
+    pn.refSlot = ref_slot;
     pn.toHost = toHost;
     if (toHost) pn.host = *out;
     PassDesc &d = c->hPasses[c->inflight.size() + c->queued.size()];  // slot stays untouched until ame_sync
@@ -293,17 +312,21 @@ int ame_flush(ame_ctx *c) {
     kp.cvtRule = c->cvtRule; kp.fusedBacksub = c->fusedBacksub; kp.earlyExit = c->earlyExit;
     kp.passes = c->dPasses + first;
     kp.bigTab = c->dBig; kp.smallTab = c->dSmall; kp.nBig = c->nBig; kp.nSmall = c->nSmall;
+    CU_TRY(cudaStreamWaitEvent(c->stream, c->evUp, 0));  // every plane uploaded so far is ready (no-op if none)
     CU_TRY(cudaEventRecord(c->evStart, c->stream));
     c->lastLaunches = launch_search(kp, c->stream, c->side, c->evFork, c->evJoin);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(c->evStop, c->stream));
+    CU_TRY(cudaEventRecord(c->evKernels, c->stream));
+    c->kernelsRecorded = true;
+    CU_TRY(cudaStreamWaitEvent(c->down, c->evKernels, 0));
     c->timed = true;
     for (const Pending &p : c->queued) {
         if (p.toHost) {
             const ResultBlock &r = c->results[p.resultIdx];
             for (int k = 0; k < 4; k++) {
-                CU_TRY(cudaMemcpyAsync(p.host.cost[k], r.cost[k], c->lens[k] * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-                CU_TRY(cudaMemcpyAsync(p.host.cpmvs[k], r.cpmvs[k], c->lens[k] * sizeof(ame_cpmvs), cudaMemcpyDeviceToHost, c->stream));
+                CU_TRY(cudaMemcpyAsync(p.host.cost[k], r.cost[k], c->lens[k] * sizeof(long long), cudaMemcpyDeviceToHost, c->down));
+                CU_TRY(cudaMemcpyAsync(p.host.cpmvs[k], r.cpmvs[k], c->lens[k] * sizeof(ame_cpmvs), cudaMemcpyDeviceToHost, c->down));
             }
         }
         c->inflight.push_back(p);
@@ -317,7 +340,9 @@ int ame_sync(ame_ctx *c) {
     int rc = ame_flush(c);
     if (rc) return rc;
     CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaStreamSynchronize(c->up));
     CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(cudaStreamSynchronize(c->down));
     c->inflight.clear();
     return AME_OK;
 }
@@ -336,12 +361,18 @@ int ame_timer_start(ame_ctx *c) {
     if (!c) return fail(AME_E_INVALID, "ame_timer_start: ctx is NULL");
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaEventRecord(c->evT0, c->stream));
+    CU_TRY(cudaStreamWaitEvent(c->up, c->evT0, 0));    // work issued from now on starts after the start mark
+    CU_TRY(cudaStreamWaitEvent(c->down, c->evT0, 0));
     return AME_OK;
 }
 
 int ame_timer_stop(ame_ctx *c, float *ms) {
     if (!c || !ms) return fail(AME_E_INVALID, "ame_timer_stop: NULL argument");
     CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaEventRecord(c->evAux, c->up));          // the stop mark follows everything on all three streams
+    CU_TRY(cudaStreamWaitEvent(c->stream, c->evAux, 0));
+    CU_TRY(cudaEventRecord(c->evAux, c->down));
+    CU_TRY(cudaStreamWaitEvent(c->stream, c->evAux, 0));
     CU_TRY(cudaEventRecord(c->evT1, c->stream));
     CU_TRY(cudaEventSynchronize(c->evT1));
     CU_TRY(cudaEventElapsedTime(ms, c->evT0, c->evT1));
