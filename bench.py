@@ -39,6 +39,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 W, H, N_FRAMES = 1920, 1080, 64
 QPS = (22, 27, 32, 37)
+WORKLOAD = "synthetic 1080p 10-bit, 64 frames with global zoom/rotation, QP sweep 22/27/32/37 (one QP per step)"
 N_CTUS = 135
 # S = sum over in-frame CUs of w*h; OPS = S * (11*40.2 + 5*45 + 4*71) int32 lane-ops per pass
 S_1080P = 42585600
@@ -190,7 +191,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "1080p frames/sec affine ME", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-            "config": {"workload": "synthetic 1080p 10-bit affine sequence, QP 32", "frames": N_FRAMES, "passes_per_frame": 250.0 / N_FRAMES},
+            "config": {"workload": WORKLOAD, "frames_per_step": N_FRAMES, "ref_passes_per_step": 250,
+                       "note": "CPU arm: each step times a bounded sample of this workload (see cpu_baseline.sample)"},
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "ref_passes_per_s": v * 250.0 / N_FRAMES}
@@ -325,7 +327,7 @@ def run_b200(args, rank, world, local_rank):
             "metric": "1080p frames/sec affine ME", "value": frames_per_s, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-            "config": {"workload": "synthetic 1080p 10-bit, 64 frames with global zoom/rotation, QP sweep 22/27/32/37 (one QP per step)",
+            "config": {"workload": WORKLOAD,
                        "frames_per_step": N_FRAMES, "ref_passes_per_step": n_pass, "per_gpu": "same sequence on every rank",
                        "l2": "inputs (1.35 GB of planes per step) larger than L2; no flush"},
             "ref_passes_per_s": passes_per_s,
