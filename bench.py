@@ -321,6 +321,11 @@ def run_b200(args, rank, world, local_rank):
         sm_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
         peak_tops = 148 * 4 * 32 * sm_mhz * 1e6 / 1e12
         per_gpu_passes = passes_per_s / world
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["dram_bytes_per_ref_pass"] * n_pass
+        except Exception:
+            pass
         achieved = OPS_PER_PASS * per_gpu_passes / 1e12
         cb_fps, cb_pps, cb_dt, cores = cpu_port_rate(orig, recon[32], 32, N_CTUS // 15)
         line = {
@@ -337,7 +342,9 @@ def run_b200(args, rank, world, local_rank):
             "gpu_launches_e2e_per_step": (N_FRAMES // CHUNK) * launches_per_flush + 3 * N_FRAMES,
             "clocks": clocks,
             "roofline": {"bound": "int32_issue", "achieved": achieved, "peak": peak_tops, "unit": "Tlane-op/s",
-                         "frac": achieved / peak_tops, "traffic": None,
+                         "frac": achieved / peak_tops, "traffic": traffic,
+                         "traffic_note": "DRAM bytes per launch pair (= per step of 250 passes), extrapolated from the ncu --set full capture "
+                                         "recorded in profiles/r01_traffic.json; algorithmic bytes per step = %d" % (ALGO_BYTES_PER_PASS * n_pass),
                          "note": "SURVEY 8(d): compute-bound on INT32 issue; achieved = as-written op model (%.1f G lane-ops/pass) x "
                                  "passes/s per GPU; peak = 148 SM x 4 x 32 lanes x %.0f MHz sampled during the run; algorithmic DRAM "
                                  "bytes/pass = %d (%.1f GB/s, vs %.0f GB/s measured HBM peak)" % (
