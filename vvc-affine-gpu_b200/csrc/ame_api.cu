@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -185,7 +186,10 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
     }
     CTX_TRY(cudaMalloc(&c->dPasses, sizeof(PassDesc) * max_in_flight));
     CTX_TRY(cudaHostAlloc(&c->hPasses, sizeof(PassDesc) * max_in_flight, cudaHostAllocDefault));
-    const CtuSchedule sched = build_schedule();
+    // Development knob: largest CU area that is processed two-per-warp (256 = only 16x16, 512, 1024).
+    int pairMax = 1024;
+    if (const char *e = getenv("AME_PAIR_MAX_AREA")) pairMax = atoi(e);
+    const CtuSchedule sched = build_schedule(pairMax);
     c->nBig = (int)sched.big.size();
     c->nSmall = (int)sched.small.size();
     CTX_TRY(cudaMalloc(&c->dBig, sizeof(uint32_t) * c->nBig));

@@ -80,7 +80,7 @@ inline uint32_t pack_cu(const CuDesc &c) {
 
 // Schedule of one CTU:
 //   big   : CUs with >= 256 4x4 sub-blocks, one 256-thread CTA each (9 per CTU)
-//   small : everything else, one warp each, largest first; 16x16 CUs are paired
+//   small : everything else, one warp each, largest first; the smallest CUs are paired
 //           (two CUs per warp, one per half-warp).  second == 0 means "no partner".
 struct SmallTask { uint32_t first, second; };
 struct CtuSchedule {
@@ -88,21 +88,28 @@ struct CtuSchedule {
     std::vector<SmallTask> small;
 };
 
-inline CtuSchedule build_schedule() {
+inline CtuSchedule build_schedule(int pairMaxArea = 256) {
     CtuSchedule s;
     std::vector<CuDesc> all = ctu_cus(0);
     std::vector<CuDesc> h = ctu_cus(1);
     all.insert(all.end(), h.begin(), h.end());
     for (int area = 128 * 128; area >= 256; area >>= 1) {
-        std::vector<CuDesc> pend16;
-        for (const CuDesc &c : all) {
-            if (c.w * c.h != area) continue;
-            if (area >= 64 * 64) s.big.push_back(pack_cu(c));
-            else if (area > 256) s.small.push_back({pack_cu(c), 0u});
-            else pend16.push_back(c);
+        // CUs of one area class; those up to pairMaxArea are paired (two CUs of the same shape per warp, one per
+        // half warp) with their successor of the same alignment class and size group, i.e. a geometric neighbour.
+        std::vector<CuDesc> cls;
+        for (const CuDesc &c : all)
+            if (c.w * c.h == area) cls.push_back(c);
+        for (size_t i = 0; i < cls.size(); i++) {
+            const CuDesc &c = cls[i];
+            if (area >= 64 * 64) {
+                s.big.push_back(pack_cu(c));
+            } else if (area <= pairMaxArea && i + 1 < cls.size() && cls[i + 1].ha == c.ha && cls[i + 1].group == c.group) {
+                s.small.push_back({pack_cu(c), pack_cu(cls[i + 1])});
+                i++;
+            } else {
+                s.small.push_back({pack_cu(c), 0u});
+            }
         }
-        for (size_t i = 0; i + 1 < pend16.size(); i += 2) s.small.push_back({pack_cu(pend16[i]), pack_cu(pend16[i + 1])});
-        if (pend16.size() & 1) s.small.push_back({pack_cu(pend16.back()), 0u});
     }
     return s;
 }
