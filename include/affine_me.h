@@ -82,8 +82,10 @@ enum {
                                   0 = x86 cvttsd2si (what it does on a CPU OpenCL device) */
     AME_OPT_FUSED_BACKSUB = 2, /* 1 (default) = back-substitution accumulates with FMA, as OpenCL's
                                   default FP_CONTRACT ON compiles affine.cl:851 */
-    AME_OPT_EARLY_EXIT = 3     /* 1 (default) = stop a CU's refinement once its CPMVs revisit an
+    AME_OPT_EARLY_EXIT = 3,    /* 1 (default) = stop a CU's refinement once its CPMVs revisit an
                                   already evaluated state (results are identical either way) */
+    AME_OPT_PIPELINE = 4       /* 1 (default) = one launch per search iteration with the per-CU FP64 solve batched one
+                                  CU per lane; 0 = one fused kernel per CU (results are identical either way) */
 };
 
 typedef struct ame_ctx ame_ctx;

@@ -43,6 +43,8 @@ struct ResultBlock {  // one per in-flight search, device memory
     char *base = nullptr;
     long long *cost[4];
     ame_cpmvs *cpmvs[4];
+    CuState *state = nullptr;  // pipelined path: per-CU search state and per-iteration accumulators
+    CuAccum *accum = nullptr;
 };
 
 struct Pending {
@@ -54,7 +56,9 @@ struct Pending {
 struct ame_ctx {
     int device = 0, W = 0, H = 0, nCtus = 0, ctuCols = 0, padStride = 0;
     int numSlots = 0, maxInFlight = 0;
-    int cvtRule = 1, fusedBacksub = 1, earlyExit = 1;
+    int cvtRule = 1, fusedBacksub = 1, earlyExit = 1, pipeline = 1;
+    int queuedExtra = 0;
+    uint32_t *dSlotTab = nullptr;
     cudaStream_t stream = nullptr, side = nullptr;  // search kernels (big CUs / small CUs)
     cudaStream_t up = nullptr, down = nullptr;      // plane uploads + preparation / result copies
     cudaEvent_t evUp = nullptr, evKernels = nullptr, evAux = nullptr;
@@ -108,6 +112,7 @@ void ame_destroy(ame_ctx *c) {
     for (Slot &s : c->slots) { cudaFree(s.raw); cudaFree(s.phase); }
     cudaFree(c->padScratch);
     for (ResultBlock &r : c->results) cudaFree(r.base);
+    cudaFree(c->dSlotTab);
     cudaFree(c->dPasses);
     cudaFree(c->dBig);
     cudaFree(c->dSmall);
@@ -176,6 +181,11 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
     size_t off[8], total = 0;
     for (int p = 0; p < 4; p++) { off[p] = total; total += (c->lens[p] * sizeof(long long) + 255) & ~(size_t)255; }
     for (int p = 0; p < 4; p++) { off[4 + p] = total; total += (c->lens[p] * sizeof(ame_cpmvs) + 255) & ~(size_t)255; }
+    const size_t nSlots = (size_t)c->nCtus * kSlotsPerCtu;
+    const size_t offState = total;
+    total += (nSlots * sizeof(CuState) + 255) & ~(size_t)255;
+    const size_t offAccum = total;
+    total += (nSlots * sizeof(CuAccum) + 255) & ~(size_t)255;
     c->results.resize(max_in_flight);
     for (ResultBlock &r : c->results) {
         CTX_TRY(cudaMalloc(&r.base, total));
@@ -183,6 +193,8 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
             r.cost[p] = reinterpret_cast<long long *>(r.base + off[p]);
             r.cpmvs[p] = reinterpret_cast<ame_cpmvs *>(r.base + off[4 + p]);
         }
+        r.state = reinterpret_cast<CuState *>(r.base + offState);
+        r.accum = reinterpret_cast<CuAccum *>(r.base + offAccum);
     }
     CTX_TRY(cudaMalloc(&c->dPasses, sizeof(PassDesc) * max_in_flight));
     CTX_TRY(cudaHostAlloc(&c->hPasses, sizeof(PassDesc) * max_in_flight, cudaHostAllocDefault));
@@ -195,6 +207,13 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
     CTX_TRY(cudaMalloc(&c->dBig, sizeof(uint32_t) * c->nBig));
     CTX_TRY(cudaMalloc(&c->dSmall, sizeof(uint2) * c->nSmall));
     CTX_TRY(cudaMemcpy(c->dBig, sched.big.data(), sizeof(uint32_t) * c->nBig, cudaMemcpyHostToDevice));
+    {   // packed CU word of every slot (aligned result index 0..200, then half-aligned 0..283)
+        std::vector<uint32_t> slotTab;
+        for (int ha = 0; ha < 2; ha++)
+            for (const CuDesc &d : ctu_cus(ha)) slotTab.push_back(pack_cu(d));
+        CTX_TRY(cudaMalloc(&c->dSlotTab, sizeof(uint32_t) * slotTab.size()));
+        CTX_TRY(cudaMemcpy(c->dSlotTab, slotTab.data(), sizeof(uint32_t) * slotTab.size(), cudaMemcpyHostToDevice));
+    }
     static_assert(sizeof(SmallTask) == sizeof(uint2), "SmallTask layout");
     CTX_TRY(cudaMemcpy(c->dSmall, sched.small.data(), sizeof(uint2) * c->nSmall, cudaMemcpyHostToDevice));
 #undef CTX_TRY
@@ -213,6 +232,7 @@ int ame_set_option(ame_ctx *c, int option, int value) {
         case AME_OPT_CVT_RULE: c->cvtRule = value ? 1 : 0; return AME_OK;
         case AME_OPT_FUSED_BACKSUB: c->fusedBacksub = value ? 1 : 0; return AME_OK;
         case AME_OPT_EARLY_EXIT: c->earlyExit = value ? 1 : 0; return AME_OK;
+        case AME_OPT_PIPELINE: c->pipeline = value ? 1 : 0; return AME_OK;
     }
     return fail(AME_E_INVALID, "ame_set_option: unknown option %d", option);
 }
@@ -254,6 +274,8 @@ int ame_upload_plane(ame_ctx *c, int slot, const uint16_t *plane) {
 static int queue_search(ame_ctx *c, int cur_slot, int ref_slot, float lambda, int extra_iters, bool toHost, const ame_result *out, int resultIdx) {
     if (cur_slot < 0 || cur_slot >= c->numSlots || ref_slot < 0 || ref_slot >= c->numSlots) return fail(AME_E_INVALID, "ame_search: slot out of range");
     if (extra_iters < 0 || extra_iters > 64) return fail(AME_E_INVALID, "ame_search: extra_iters %d out of range", extra_iters);
+    if (!c->queued.empty() && extra_iters != c->queuedExtra) { int rc = ame_flush(c); if (rc) return rc; }  // one launch sequence = one iteration count
+    c->queuedExtra = extra_iters;
     if (!c->slots[ref_slot].hasRef) return fail(AME_E_STATE, "ame_search: slot %d was not uploaded with the reference role", ref_slot);
     if ((int)(c->queued.size() + c->inflight.size()) >= c->maxInFlight) return fail(AME_E_STATE, "ame_search: %d searches already in flight; call ame_sync", c->maxInFlight);
     if (resultIdx < 0) {
@@ -279,6 +301,8 @@ static int queue_search(ame_ctx *c, int cur_slot, int ref_slot, float lambda, in
     for (int p = 0; p < 4; p++) { d.cost[p] = c->results[resultIdx].cost[p]; d.cpmvs[p] = c->results[resultIdx].cpmvs[p]; }
     d.lambda = lambda;
     d.extraIter = extra_iters;
+    d.state = c->results[resultIdx].state;
+    d.accum = c->results[resultIdx].accum;
     c->queued.push_back(pn);
     return AME_OK;
 }
@@ -316,9 +340,11 @@ int ame_flush(ame_ctx *c) {
     kp.cvtRule = c->cvtRule; kp.fusedBacksub = c->fusedBacksub; kp.earlyExit = c->earlyExit;
     kp.passes = c->dPasses + first;
     kp.bigTab = c->dBig; kp.smallTab = c->dSmall; kp.nBig = c->nBig; kp.nSmall = c->nSmall;
+    kp.slotTab = c->dSlotTab; kp.extraIter = c->queuedExtra; kp.pipeline = c->pipeline;
     CU_TRY(cudaStreamWaitEvent(c->stream, c->evUp, 0));  // every plane uploaded so far is ready (no-op if none)
     CU_TRY(cudaEventRecord(c->evStart, c->stream));
-    c->lastLaunches = launch_search(kp, c->stream, c->side, c->evFork, c->evJoin);
+    c->lastLaunches = c->pipeline ? launch_search_pipeline(kp, c->stream, c->side, c->evFork, c->evJoin)
+                                  : launch_search(kp, c->stream, c->side, c->evFork, c->evJoin);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(c->evStop, c->stream));
     CU_TRY(cudaEventRecord(c->evKernels, c->stream));

@@ -14,6 +14,21 @@ namespace ame {
 // the worst case; 160 keeps rows 64-byte aligned.
 constexpr int kPad = 160;
 
+// Per-CU search state and per-iteration accumulators of the pipelined path (ame_iter_kernel / ame_update_kernel).
+// Slot k of a CTU: aligned CUs 0..200 (result index), half-aligned CUs 201..484.
+constexpr int kSlotsPerCtu = AME_ALIGNED_CUS_PER_CTU + AME_HALF_CUS_PER_CTU;
+struct CuState {
+    int cur[6];          // CPMVs evaluated by the next / current iteration (ltx, lty, rtx, rty, lbx, lby)
+    int best[6];
+    long long bestCost;
+    int h1[6], h2[6];    // the two states evaluated before cur
+    int done, pad;
+};
+struct CuAccum {
+    long long mom[24];   // moments of the normal equations (numbering of moment3())
+    int satd, pad;
+};
+
 // One queued search, as the kernels see it.
 struct PassDesc {
     const uint16_t *cur;     // raw current plane, stride = W
@@ -23,6 +38,8 @@ struct PassDesc {
     ame_cpmvs *cpmvs[4];
     float lambda;
     int extraIter;
+    CuState *state;  // [nCtus * kSlotsPerCtu]
+    CuAccum *accum;  // [nCtus * kSlotsPerCtu]
 };
 
 struct KParams {
@@ -34,10 +51,15 @@ struct KParams {
     const uint32_t *bigTab;   // device array [nBig] packed CU words
     const uint2 *smallTab;    // device array [nSmall] (first, second) packed CU words
     int nBig, nSmall;
+    const uint32_t *slotTab;  // device array [kSlotsPerCtu]: packed CU word of every slot
+    int extraIter;            // --ExtraGradientIter of this batch (uniform per launch sequence)
+    int pipeline;             // 1: iteration-per-launch path, 0: fused per-CU kernel
 };
 
 // Launches the search kernels for all passes on `stream`; returns launches made.
 int launch_search(const KParams &kp, cudaStream_t stream, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);
+// Same result through the iteration-per-launch pipeline (ame_iter_kernel / ame_update_kernel / ame_phase_kernel).
+int launch_search_pipeline(const KParams &kp, cudaStream_t stream, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);
 // dst (padded, stride padStride) <- edge-replicated src (W x H).
 void launch_pad(const uint16_t *src, uint16_t *dst, int W, int H, int padStride, cudaStream_t stream);
 // phase[16][H + 2*kPad][padStride] <- first interpolation stage of the padded plane `pad`, all 16 phases.
