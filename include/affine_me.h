@@ -82,10 +82,8 @@ enum {
                                   0 = x86 cvttsd2si (what it does on a CPU OpenCL device) */
     AME_OPT_FUSED_BACKSUB = 2, /* 1 (default) = back-substitution accumulates with FMA, as OpenCL's
                                   default FP_CONTRACT ON compiles affine.cl:851 */
-    AME_OPT_EARLY_EXIT = 3,    /* 1 (default) = stop a CU's refinement once its CPMVs revisit an
+    AME_OPT_EARLY_EXIT = 3     /* 1 (default) = stop a CU's refinement once its CPMVs revisit an
                                   already evaluated state (results are identical either way) */
-    AME_OPT_PIPELINE = 4       /* 1 (default) = one launch per search iteration with the per-CU FP64 solve batched one
-                                  CU per lane; 0 = one fused kernel per CU (results are identical either way) */
 };
 
 typedef struct ame_ctx ame_ctx;
@@ -108,10 +106,11 @@ int ame_set_option(ame_ctx *ctx, int option, int value);
  * until the next ame_sync; pinned memory makes the copy truly asynchronous. */
 int ame_upload_plane(ame_ctx *ctx, int slot, const uint16_t *plane);
 
-/* Same with an explicit role mask.  AME_ROLE_CURRENT: the plane will be searched FOR (original frames);
- * AME_ROLE_REFERENCE: the plane will be searched IN (reconstructed frames) -- this runs the horizontal
- * interpolation stage for all 16 phases once and keeps the result (16 x (W+320) x (H+320) x 4 bytes of device
- * memory, allocated on the slot's first reference upload).  ame_upload_plane gives both roles. */
+/* Same with an explicit role mask.  AME_ROLE_CURRENT: the plane will be searched FOR (original frames; kept a
+ * second time in 4x4-block order); AME_ROLE_REFERENCE: the plane will be searched IN (reconstructed frames) -- this
+ * runs the horizontal interpolation stage for all 16 phases once and keeps the result in four column alignments
+ * (4 x 16 x (W+320) x (H+320) x 2 bytes of device memory, allocated on the slot's first reference upload).
+ * ame_upload_plane gives both roles; ame_search fails with AME_E_STATE on a slot that lacks the role it needs. */
 enum { AME_ROLE_CURRENT = 1, AME_ROLE_REFERENCE = 2 };
 int ame_upload_plane_ex(ame_ctx *ctx, int slot, const uint16_t *plane, int roles);
 

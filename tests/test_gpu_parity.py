@@ -124,26 +124,6 @@ def test_early_exit_is_exact(pkg):
     assert _diff(out[0][0], out[0][1], out[1][0], out[1][1]) == 0
 
 
-def test_fused_and_pipelined_paths_agree(pkg):
-    """AME_OPT_PIPELINE: the fused per-CU kernel and the iteration-per-launch pipeline are two schedules of the same
-    arithmetic; both must reproduce the reference (here: each other and the oracle) bit for bit, with and without
-    extra iterations."""
-    orig, recon = sf.sequences(1, 832, 480, 27, seed=sf.SEED + 51)
-    lam = ob.lambda_for(27, 1)
-    for extra in (0, 2):
-        out = []
-        for mode in (1, 0):
-            ctx = pkg.AffineME(832, 480)
-            try:
-                ctx.set_option(pkg.OPT_PIPELINE, mode)
-                out.append(ctx.ref_pass(recon[0], orig[0], lam, extra))
-            finally:
-                ctx.close()
-        assert _diff(out[0][0], out[0][1], out[1][0], out[1][1]) == 0
-        oc, om = ob.ref_pass(recon[0], orig[0], lam, ob.default_opts(extra_iter=extra))
-        assert _diff(out[0][0], out[0][1], oc, om) == 0
-
-
 def test_1080p_properties(pkg):
     """Full-size checks: batched == one-by-one, run-to-run determinism, the fixed rows of out-of-frame CUs, and
     CTU row 0 against the oracle run on a 1920x256 strip (row 0's searches never reach the strip's bottom edge,

@@ -21,7 +21,7 @@ for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz"))):
     orig, recon, qp, extra = d["orig"], d["recon"], int(d["qp"]), int(d["extra_iter"])
     n, H, W = orig.shape
     ctx = pkg.AffineME(W, H)
-    ctx.set_option(pkg.OPT_PIPELINE, int(os.environ.get('AME_PIPELINE', '1')))
+    
     lists = ob.ref_lists(n)
     bad = tot = 0
     t0 = time.time()

@@ -19,7 +19,6 @@ ap.add_argument("--frames", type=int, default=4)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--size", default="1920x1080")
 ap.add_argument("--early-exit", type=int, default=1)
-ap.add_argument("--pipeline", type=int, default=1)
 a = ap.parse_args()
 W, H = [int(x) for x in a.size.split("x")]
 pkg = load_pkg()
@@ -28,7 +27,6 @@ lists = bench.ref_lists(a.frames)
 passes = [(poc, r, lists[poc - 1][r]) for poc in range(1, a.frames + 1) for r in range(len(lists[poc - 1]))]
 ctx = pkg.AffineME(W, H, num_slots=2 * a.frames, max_in_flight=len(passes))
 ctx.set_option(pkg.OPT_EARLY_EXIT, a.early_exit)
-ctx.set_option(pkg.OPT_PIPELINE, a.pipeline)
 for f in range(a.frames):
     ctx.upload(f, orig[f])
     ctx.upload(a.frames + f, recon[f])

@@ -34,16 +34,17 @@ static int fail(int code, const char *fmt, ...) {
     } while (0)
 
 struct Slot {
-    uint16_t *raw = nullptr;    // W x H, current-frame role
-    uint32_t *phase = nullptr;  // 16 pre-filtered phase planes, reference role; allocated on first use
-    bool hasRef = false;        // phase planes match the current contents of raw
+    uint16_t *raw = nullptr;    // W x H, as uploaded
+    uint4 *blk = nullptr;       // current-frame role: the plane in 4x4-block order; allocated on first use
+    uint2 *refT = nullptr;      // reference role: 4 x 16 pre-filtered planes; allocated on first use
+    bool hasCur = false, hasRef = false;  // blk / refT match the current contents of raw
 };
 
 struct ResultBlock {  // one per in-flight search, device memory
     char *base = nullptr;
     long long *cost[4];
     ame_cpmvs *cpmvs[4];
-    CuState *state = nullptr;  // pipelined path: per-CU search state and per-iteration accumulators
+    CuState *state = nullptr;  // per-CU search state and per-iteration accumulators
     CuAccum *accum = nullptr;
 };
 
@@ -56,7 +57,7 @@ struct Pending {
 struct ame_ctx {
     int device = 0, W = 0, H = 0, nCtus = 0, ctuCols = 0, padStride = 0;
     int numSlots = 0, maxInFlight = 0;
-    int cvtRule = 1, fusedBacksub = 1, earlyExit = 1, pipeline = 1;
+    int cvtRule = 1, fusedBacksub = 1, earlyExit = 1;
     int queuedExtra = 0;
     uint32_t *dSlotTab = nullptr;
     cudaStream_t stream = nullptr, side = nullptr;  // search kernels (big CUs / small CUs)
@@ -67,7 +68,8 @@ struct ame_ctx {
     bool timed = false;
     int lastLaunches = 0;
     uint16_t *padScratch = nullptr;  // (W + 2*kPad) x (H + 2*kPad) edge-replicated plane, input of the phase filter
-    size_t planeElems = 0;
+    size_t planeElems = 0;  // samples of the padded plane
+    size_t planeRecs = 0;   // 8-byte records per (copy, phase) plane of refT
     std::vector<Slot> slots;
     std::vector<ResultBlock> results;
     PassDesc *dPasses = nullptr;   // device [maxInFlight]
@@ -109,7 +111,7 @@ void ame_destroy(ame_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (cudaStream_t s : {c->up, c->stream, c->side, c->down}) if (s) cudaStreamSynchronize(s);
-    for (Slot &s : c->slots) { cudaFree(s.raw); cudaFree(s.phase); }
+    for (Slot &s : c->slots) { cudaFree(s.raw); cudaFree(s.blk); cudaFree(s.refT); }
     cudaFree(c->padScratch);
     for (ResultBlock &r : c->results) cudaFree(r.base);
     cudaFree(c->dSlotTab);
@@ -176,6 +178,7 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
     c->slots.resize(num_slots);
     const size_t rawBytes = (size_t)width * height * sizeof(uint16_t);
     c->planeElems = (size_t)c->padStride * (height + 2 * kPad);
+    c->planeRecs = (size_t)(c->padStride / 4) * (height + 2 * kPad);
     CTX_TRY(cudaMalloc(&c->padScratch, c->planeElems * sizeof(uint16_t) + 64));
     for (Slot &s : c->slots) CTX_TRY(cudaMalloc(&s.raw, rawBytes));
     size_t off[8], total = 0;
@@ -232,7 +235,6 @@ int ame_set_option(ame_ctx *c, int option, int value) {
         case AME_OPT_CVT_RULE: c->cvtRule = value ? 1 : 0; return AME_OK;
         case AME_OPT_FUSED_BACKSUB: c->fusedBacksub = value ? 1 : 0; return AME_OK;
         case AME_OPT_EARLY_EXIT: c->earlyExit = value ? 1 : 0; return AME_OK;
-        case AME_OPT_PIPELINE: c->pipeline = value ? 1 : 0; return AME_OK;
     }
     return fail(AME_E_INVALID, "ame_set_option: unknown option %d", option);
 }
@@ -252,14 +254,23 @@ int ame_upload_plane_ex(ame_ctx *c, int slot, const uint16_t *plane, int roles) 
     if (inflightUse && c->kernelsRecorded) CU_TRY(cudaStreamWaitEvent(c->up, c->evKernels, 0));
     Slot &s = c->slots[slot];
     CU_TRY(cudaMemcpyAsync(s.raw, plane, (size_t)c->W * c->H * sizeof(uint16_t), cudaMemcpyHostToDevice, c->up));
-    s.hasRef = false;
+    s.hasRef = s.hasCur = false;
+    if (roles & AME_ROLE_CURRENT) {
+        if (!s.blk) {
+            cudaError_t e = cudaMalloc(&s.blk, (size_t)(c->W / 4) * ((c->H + 3) / 4) * 2 * sizeof(uint4));
+            if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? AME_E_NOMEM : AME_E_CUDA, "block-ordered plane of slot %d: %s", slot, cudaGetErrorString(e));
+        }
+        launch_block_plane(s.raw, s.blk, c->W, c->H, c->up);
+        CU_TRY(cudaGetLastError());
+        s.hasCur = true;
+    }
     if (roles & AME_ROLE_REFERENCE) {
-        if (!s.phase) {
-            cudaError_t e = cudaMalloc(&s.phase, 16 * c->planeElems * sizeof(uint32_t));
-            if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? AME_E_NOMEM : AME_E_CUDA, "phase planes of slot %d: %s", slot, cudaGetErrorString(e));
+        if (!s.refT) {
+            cudaError_t e = cudaMalloc(&s.refT, 4 * 16 * c->planeRecs * sizeof(uint2));
+            if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? AME_E_NOMEM : AME_E_CUDA, "pre-filtered planes of slot %d: %s", slot, cudaGetErrorString(e));
         }
         launch_pad(s.raw, c->padScratch, c->W, c->H, c->padStride, c->up);
-        launch_phase_planes(c->padScratch, s.phase, c->W, c->H, c->padStride, c->up);
+        launch_phase_planes(c->padScratch, s.refT, c->W, c->H, c->padStride, c->up);
         CU_TRY(cudaGetLastError());
         s.hasRef = true;
     }
@@ -277,6 +288,7 @@ static int queue_search(ame_ctx *c, int cur_slot, int ref_slot, float lambda, in
     if (!c->queued.empty() && extra_iters != c->queuedExtra) { int rc = ame_flush(c); if (rc) return rc; }  // one launch sequence = one iteration count
     c->queuedExtra = extra_iters;
     if (!c->slots[ref_slot].hasRef) return fail(AME_E_STATE, "ame_search: slot %d was not uploaded with the reference role", ref_slot);
+    if (!c->slots[cur_slot].hasCur) return fail(AME_E_STATE, "ame_search: slot %d was not uploaded with the current-frame role", cur_slot);
     if ((int)(c->queued.size() + c->inflight.size()) >= c->maxInFlight) return fail(AME_E_STATE, "ame_search: %d searches already in flight; call ame_sync", c->maxInFlight);
     if (resultIdx < 0) {
         // first result block not used by a queued / in-flight search
@@ -296,8 +308,8 @@ static int queue_search(ame_ctx *c, int cur_slot, int ref_slot, float lambda, in
     pn.toHost = toHost;
     if (toHost) pn.host = *out;
     PassDesc &d = c->hPasses[c->inflight.size() + c->queued.size()];  // slot stays untouched until ame_sync
-    d.cur = c->slots[cur_slot].raw;
-    d.refPhase = c->slots[ref_slot].phase;
+    d.curBlk = c->slots[cur_slot].blk;
+    d.refT = c->slots[ref_slot].refT;
     for (int p = 0; p < 4; p++) { d.cost[p] = c->results[resultIdx].cost[p]; d.cpmvs[p] = c->results[resultIdx].cpmvs[p]; }
     d.lambda = lambda;
     d.extraIter = extra_iters;
@@ -335,16 +347,15 @@ int ame_flush(ame_ctx *c) {
     CU_TRY(cudaMemcpyAsync(c->dPasses + first, c->hPasses + first, sizeof(PassDesc) * n, cudaMemcpyHostToDevice, c->stream));
     KParams kp;
     kp.W = c->W; kp.H = c->H; kp.ctuCols = c->ctuCols; kp.nCtus = c->nCtus; kp.padStride = c->padStride;
-    kp.planeElems = c->planeElems;
+    kp.planeRecs = c->planeRecs;
     kp.nPasses = n;
     kp.cvtRule = c->cvtRule; kp.fusedBacksub = c->fusedBacksub; kp.earlyExit = c->earlyExit;
     kp.passes = c->dPasses + first;
     kp.bigTab = c->dBig; kp.smallTab = c->dSmall; kp.nBig = c->nBig; kp.nSmall = c->nSmall;
-    kp.slotTab = c->dSlotTab; kp.extraIter = c->queuedExtra; kp.pipeline = c->pipeline;
+    kp.slotTab = c->dSlotTab; kp.extraIter = c->queuedExtra;
     CU_TRY(cudaStreamWaitEvent(c->stream, c->evUp, 0));  // every plane uploaded so far is ready (no-op if none)
     CU_TRY(cudaEventRecord(c->evStart, c->stream));
-    c->lastLaunches = c->pipeline ? launch_search_pipeline(kp, c->stream, c->side, c->evFork, c->evJoin)
-                                  : launch_search(kp, c->stream, c->side, c->evFork, c->evJoin);
+    c->lastLaunches = launch_search(kp, c->stream, c->side, c->evFork, c->evJoin);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(c->evStop, c->stream));
     CU_TRY(cudaEventRecord(c->evKernels, c->stream));

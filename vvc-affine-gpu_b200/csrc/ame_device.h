@@ -14,7 +14,7 @@ namespace ame {
 // the worst case; 160 keeps rows 64-byte aligned.
 constexpr int kPad = 160;
 
-// Per-CU search state and per-iteration accumulators of the pipelined path (ame_iter_kernel / ame_update_kernel).
+// Per-CU search state and per-iteration accumulators (ame_iter_kernel / ame_update_kernel).
 // Slot k of a CTU: aligned CUs 0..200 (result index), half-aligned CUs 201..484.
 constexpr int kSlotsPerCtu = AME_ALIGNED_CUS_PER_CTU + AME_HALF_CUS_PER_CTU;
 struct CuState {
@@ -25,15 +25,15 @@ struct CuState {
     int done, pad;
 };
 struct CuAccum {
-    long long mom[24];   // moments of the normal equations (numbering of moment3())
+    long long mom[24];   // moments of the normal equations (numbering of kMomOf in ame_kernels.cu)
     int satd, pad;
 };
 
 // One queued search, as the kernels see it.
 struct PassDesc {
-    const uint16_t *cur;     // raw current plane, stride = W
-    const uint32_t *refPhase;  // 16 pre-filtered phase planes of the reference (launch_phase_planes), each padStride x
-                               // (H + 2*kPad) pair words, (0,0) of the frame at [kPad][kPad]
+    const uint4 *curBlk;     // current plane in 4x4-block order (launch_block_plane): 2 x uint4 per block
+    const uint2 *refT;       // first-stage rows of the reference (launch_phase_planes): [4 copies][16 phases] planes of
+                             // (H + 2*kPad) rows x padStride/4 records, (0,0) of the frame at sample [kPad][kPad]
     long long *cost[4];
     ame_cpmvs *cpmvs[4];
     float lambda;
@@ -44,7 +44,7 @@ struct PassDesc {
 
 struct KParams {
     int W, H, ctuCols, nCtus, padStride;
-    size_t planeElems;  // padStride * (H + 2*kPad): words per phase plane
+    size_t planeRecs;   // (padStride / 4) * (H + 2*kPad): 8-byte records per (copy, phase) plane
     int nPasses;
     int cvtRule, fusedBacksub, earlyExit;
     const PassDesc *passes;   // device array [nPasses]
@@ -53,17 +53,18 @@ struct KParams {
     int nBig, nSmall;
     const uint32_t *slotTab;  // device array [kSlotsPerCtu]: packed CU word of every slot
     int extraIter;            // --ExtraGradientIter of this batch (uniform per launch sequence)
-    int pipeline;             // 1: iteration-per-launch path, 0: fused per-CU kernel
 };
 
-// Launches the search kernels for all passes on `stream`; returns launches made.
+// Launches the search kernels (ame_phase_kernel / ame_iter_kernel / ame_update_kernel, one iteration per launch)
+// for all passes on `stream`; returns launches made.
 int launch_search(const KParams &kp, cudaStream_t stream, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);
-// Same result through the iteration-per-launch pipeline (ame_iter_kernel / ame_update_kernel / ame_phase_kernel).
-int launch_search_pipeline(const KParams &kp, cudaStream_t stream, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);
 // dst (padded, stride padStride) <- edge-replicated src (W x H).
 void launch_pad(const uint16_t *src, uint16_t *dst, int W, int H, int padStride, cudaStream_t stream);
-// phase[16][H + 2*kPad][padStride] <- first interpolation stage of the padded plane `pad`, all 16 phases.
-void launch_phase_planes(const uint16_t *pad, uint32_t *phase, int W, int H, int padStride, cudaStream_t stream);
+// refT[4][16][H + 2*kPad][padStride/4] <- first interpolation stage of the padded plane `pad`, all 16 phases, in four
+// column alignments (8-byte records of four int16).
+void launch_phase_planes(const uint16_t *pad, uint2 *refT, int W, int H, int padStride, cudaStream_t stream);
+// blk <- src (W x H) in 4x4-block order (32 bytes per block, (W/4) x ceil(H/4) blocks).
+void launch_block_plane(const uint16_t *src, uint4 *blk, int W, int H, cudaStream_t stream);
 
 // Development counters of builds with -DAME_STATS (zeros otherwise).
 void debug_stats(unsigned long long *out24, bool reset);
