@@ -36,7 +36,7 @@ static int fail(int code, const char *fmt, ...) {
 struct Slot {
     uint16_t *raw = nullptr;    // W x H, as uploaded
     uint4 *blk = nullptr;       // current-frame role: the plane in 4x4-block order; allocated on first use
-    uint2 *refT = nullptr;      // reference role: 4 x 16 pre-filtered planes; allocated on first use
+    uint32_t *refT = nullptr;   // reference role: 16 pre-filtered planes; allocated on first use
     bool hasCur = false, hasRef = false;  // blk / refT match the current contents of raw
 };
 
@@ -44,8 +44,6 @@ struct ResultBlock {  // one per in-flight search, device memory
     char *base = nullptr;
     long long *cost[4];
     ame_cpmvs *cpmvs[4];
-    CuState *state = nullptr;  // per-CU search state and per-iteration accumulators
-    CuAccum *accum = nullptr;
 };
 
 struct Pending {
@@ -59,7 +57,16 @@ struct ame_ctx {
     int numSlots = 0, maxInFlight = 0;
     int cvtRule = 1, fusedBacksub = 1, earlyExit = 1;
     int queuedExtra = 0;
+    int numSMs = 0;
     uint32_t *dSlotTab = nullptr;
+    // scratch of a launch sequence (ame_device.h): search state, accumulators and work lists for maxInFlight passes
+    CuState *dState = nullptr;
+    CuAccum *dAccum = nullptr;
+    unsigned char *dGoFlag = nullptr;
+    uint2 *dBlockCnt = nullptr, *dBlockOff = nullptr;
+    WorkLists *dWork = nullptr;
+    uint4 *dSmallList = nullptr;
+    uint2 *dBigList = nullptr;
     cudaStream_t stream = nullptr, side = nullptr;  // search kernels (big CUs / small CUs)
     cudaStream_t up = nullptr, down = nullptr;      // plane uploads + preparation / result copies
     cudaEvent_t evUp = nullptr, evKernels = nullptr, evAux = nullptr;
@@ -69,14 +76,11 @@ struct ame_ctx {
     int lastLaunches = 0;
     uint16_t *padScratch = nullptr;  // (W + 2*kPad) x (H + 2*kPad) edge-replicated plane, input of the phase filter
     size_t planeElems = 0;  // samples of the padded plane
-    size_t planeRecs = 0;   // 8-byte records per (copy, phase) plane of refT
+    size_t planeWords = 0;  // words per phase plane of refT
     std::vector<Slot> slots;
     std::vector<ResultBlock> results;
     PassDesc *dPasses = nullptr;   // device [maxInFlight]
     PassDesc *hPasses = nullptr;   // pinned [maxInFlight]
-    uint32_t *dBig = nullptr;
-    uint2 *dSmall = nullptr;
-    int nBig = 0, nSmall = 0;
     std::vector<Pending> queued;   // searches queued since the last flush
     std::vector<Pending> inflight; // launched, results not yet known complete
     size_t lens[4];
@@ -116,8 +120,14 @@ void ame_destroy(ame_ctx *c) {
     for (ResultBlock &r : c->results) cudaFree(r.base);
     cudaFree(c->dSlotTab);
     cudaFree(c->dPasses);
-    cudaFree(c->dBig);
-    cudaFree(c->dSmall);
+    cudaFree(c->dState);
+    cudaFree(c->dAccum);
+    cudaFree(c->dWork);
+    cudaFree(c->dGoFlag);
+    cudaFree(c->dBlockCnt);
+    cudaFree(c->dBlockOff);
+    cudaFree(c->dSmallList);
+    cudaFree(c->dBigList);
     if (c->hPasses) cudaFreeHost(c->hPasses);
     if (c->evStart) cudaEventDestroy(c->evStart);
     if (c->evStop) cudaEventDestroy(c->evStop);
@@ -144,6 +154,7 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
     if (device < 0 || device >= ndev) return fail(AME_E_INVALID, "ame_create: device %d out of range (%d devices)", device, ndev);
     CU_TRY(cudaSetDevice(device));
     ame_ctx *c = new ame_ctx();
+    cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, device);
     c->device = device;
     c->W = width;
     c->H = height;
@@ -178,17 +189,12 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
     c->slots.resize(num_slots);
     const size_t rawBytes = (size_t)width * height * sizeof(uint16_t);
     c->planeElems = (size_t)c->padStride * (height + 2 * kPad);
-    c->planeRecs = (size_t)(c->padStride / 4) * (height + 2 * kPad);
+    c->planeWords = (size_t)(c->padStride / 2) * (height + 2 * kPad);
     CTX_TRY(cudaMalloc(&c->padScratch, c->planeElems * sizeof(uint16_t) + 64));
     for (Slot &s : c->slots) CTX_TRY(cudaMalloc(&s.raw, rawBytes));
     size_t off[8], total = 0;
     for (int p = 0; p < 4; p++) { off[p] = total; total += (c->lens[p] * sizeof(long long) + 255) & ~(size_t)255; }
     for (int p = 0; p < 4; p++) { off[4 + p] = total; total += (c->lens[p] * sizeof(ame_cpmvs) + 255) & ~(size_t)255; }
-    const size_t nSlots = (size_t)c->nCtus * kSlotsPerCtu;
-    const size_t offState = total;
-    total += (nSlots * sizeof(CuState) + 255) & ~(size_t)255;
-    const size_t offAccum = total;
-    total += (nSlots * sizeof(CuAccum) + 255) & ~(size_t)255;
     c->results.resize(max_in_flight);
     for (ResultBlock &r : c->results) {
         CTX_TRY(cudaMalloc(&r.base, total));
@@ -196,20 +202,21 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
             r.cost[p] = reinterpret_cast<long long *>(r.base + off[p]);
             r.cpmvs[p] = reinterpret_cast<ame_cpmvs *>(r.base + off[4 + p]);
         }
-        r.state = reinterpret_cast<CuState *>(r.base + offState);
-        r.accum = reinterpret_cast<CuAccum *>(r.base + offAccum);
+    }
+    {   // scratch of one launch sequence: at most min(max_in_flight, kMaxPasses) passes
+        const size_t seqPasses = (size_t)(max_in_flight < kMaxPasses ? max_in_flight : kMaxPasses);
+        const size_t nSlots = seqPasses * c->nCtus * kSlotsPerCtu;
+        CTX_TRY(cudaMalloc(&c->dState, nSlots * sizeof(CuState)));
+        CTX_TRY(cudaMalloc(&c->dAccum, nSlots * sizeof(CuAccum)));
+        CTX_TRY(cudaMalloc(&c->dWork, sizeof(WorkLists)));
+        CTX_TRY(cudaMalloc(&c->dGoFlag, nSlots));
+        CTX_TRY(cudaMalloc(&c->dBlockCnt, ((nSlots + 127) / 128) * sizeof(uint2)));
+        CTX_TRY(cudaMalloc(&c->dBlockOff, ((nSlots + 127) / 128) * sizeof(uint2)));
+        CTX_TRY(cudaMalloc(&c->dSmallList, nSlots * sizeof(uint4)));
+        CTX_TRY(cudaMalloc(&c->dBigList, seqPasses * c->nCtus * 9 * sizeof(uint2)));
     }
     CTX_TRY(cudaMalloc(&c->dPasses, sizeof(PassDesc) * max_in_flight));
     CTX_TRY(cudaHostAlloc(&c->hPasses, sizeof(PassDesc) * max_in_flight, cudaHostAllocDefault));
-    // Development knob: largest CU area that is processed two-per-warp (256 = only 16x16, 512, 1024).
-    int pairMax = 1024;
-    if (const char *e = getenv("AME_PAIR_MAX_AREA")) pairMax = atoi(e);
-    const CtuSchedule sched = build_schedule(pairMax);
-    c->nBig = (int)sched.big.size();
-    c->nSmall = (int)sched.small.size();
-    CTX_TRY(cudaMalloc(&c->dBig, sizeof(uint32_t) * c->nBig));
-    CTX_TRY(cudaMalloc(&c->dSmall, sizeof(uint2) * c->nSmall));
-    CTX_TRY(cudaMemcpy(c->dBig, sched.big.data(), sizeof(uint32_t) * c->nBig, cudaMemcpyHostToDevice));
     {   // packed CU word of every slot (aligned result index 0..200, then half-aligned 0..283)
         std::vector<uint32_t> slotTab;
         for (int ha = 0; ha < 2; ha++)
@@ -217,8 +224,6 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
         CTX_TRY(cudaMalloc(&c->dSlotTab, sizeof(uint32_t) * slotTab.size()));
         CTX_TRY(cudaMemcpy(c->dSlotTab, slotTab.data(), sizeof(uint32_t) * slotTab.size(), cudaMemcpyHostToDevice));
     }
-    static_assert(sizeof(SmallTask) == sizeof(uint2), "SmallTask layout");
-    CTX_TRY(cudaMemcpy(c->dSmall, sched.small.data(), sizeof(uint2) * c->nSmall, cudaMemcpyHostToDevice));
 #undef CTX_TRY
     *out = c;
     return AME_OK;
@@ -266,7 +271,7 @@ int ame_upload_plane_ex(ame_ctx *c, int slot, const uint16_t *plane, int roles) 
     }
     if (roles & AME_ROLE_REFERENCE) {
         if (!s.refT) {
-            cudaError_t e = cudaMalloc(&s.refT, 4 * 16 * c->planeRecs * sizeof(uint2));
+            cudaError_t e = cudaMalloc(&s.refT, 16 * c->planeWords * sizeof(uint32_t));
             if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? AME_E_NOMEM : AME_E_CUDA, "pre-filtered planes of slot %d: %s", slot, cudaGetErrorString(e));
         }
         launch_pad(s.raw, c->padScratch, c->W, c->H, c->padStride, c->up);
@@ -313,8 +318,6 @@ static int queue_search(ame_ctx *c, int cur_slot, int ref_slot, float lambda, in
     for (int p = 0; p < 4; p++) { d.cost[p] = c->results[resultIdx].cost[p]; d.cpmvs[p] = c->results[resultIdx].cpmvs[p]; }
     d.lambda = lambda;
     d.extraIter = extra_iters;
-    d.state = c->results[resultIdx].state;
-    d.accum = c->results[resultIdx].accum;
     c->queued.push_back(pn);
     return AME_OK;
 }
@@ -347,15 +350,27 @@ int ame_flush(ame_ctx *c) {
     CU_TRY(cudaMemcpyAsync(c->dPasses + first, c->hPasses + first, sizeof(PassDesc) * n, cudaMemcpyHostToDevice, c->stream));
     KParams kp;
     kp.W = c->W; kp.H = c->H; kp.ctuCols = c->ctuCols; kp.nCtus = c->nCtus; kp.padStride = c->padStride;
-    kp.planeRecs = c->planeRecs;
-    kp.nPasses = n;
+    kp.planeWords = c->planeWords;
     kp.cvtRule = c->cvtRule; kp.fusedBacksub = c->fusedBacksub; kp.earlyExit = c->earlyExit;
-    kp.passes = c->dPasses + first;
-    kp.bigTab = c->dBig; kp.smallTab = c->dSmall; kp.nBig = c->nBig; kp.nSmall = c->nSmall;
     kp.slotTab = c->dSlotTab; kp.extraIter = c->queuedExtra;
+    kp.state = c->dState; kp.accum = c->dAccum;
+    kp.goFlag = c->dGoFlag; kp.blockCnt = c->dBlockCnt; kp.blockOff = c->dBlockOff;
+    kp.work = c->dWork; kp.smallList = c->dSmallList; kp.bigList = c->dBigList;
     CU_TRY(cudaStreamWaitEvent(c->stream, c->evUp, 0));  // every plane uploaded so far is ready (no-op if none)
     CU_TRY(cudaEventRecord(c->evStart, c->stream));
-    c->lastLaunches = launch_search(kp, c->stream, c->side, c->evFork, c->evJoin);
+    // One launch sequence per chunk of at most kMaxPasses searches (they share the scratch arrays, in stream order).
+    c->lastLaunches = 0;
+    static thread_local PassTable pt;
+    for (int k0 = 0; k0 < n; k0 += kMaxPasses) {
+        const int m = n - k0 < kMaxPasses ? n - k0 : kMaxPasses;
+        kp.nPasses = m;
+        kp.passes = c->dPasses + first + k0;
+        for (int i = 0; i < m; i++) {
+            pt.p[i].curBlk = c->hPasses[first + k0 + i].curBlk;
+            pt.p[i].refT = c->hPasses[first + k0 + i].refT;
+        }
+        c->lastLaunches += launch_search(kp, pt, c->numSMs, c->stream, c->side, c->evFork, c->evJoin);
+    }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(c->evStop, c->stream));
     CU_TRY(cudaEventRecord(c->evKernels, c->stream));

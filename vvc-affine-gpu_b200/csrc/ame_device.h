@@ -32,37 +32,54 @@ struct CuAccum {
 // One queued search, as the kernels see it.
 struct PassDesc {
     const uint4 *curBlk;     // current plane in 4x4-block order (launch_block_plane): 2 x uint4 per block
-    const uint2 *refT;       // first-stage rows of the reference (launch_phase_planes): [4 copies][16 phases] planes of
-                             // (H + 2*kPad) rows x padStride/4 records, (0,0) of the frame at sample [kPad][kPad]
+    const uint32_t *refT;    // first-stage rows of the reference (launch_phase_planes): 16 phase planes of
+                             // (H + 2*kPad) rows x padStride/2 words of two int16, (0,0) of the frame at sample [kPad][kPad]
     long long *cost[4];
     ame_cpmvs *cpmvs[4];
     float lambda;
     int extraIter;
-    CuState *state;  // [nCtus * kSlotsPerCtu]
-    CuAccum *accum;  // [nCtus * kSlotsPerCtu]
+};
+
+// The two plane pointers of every pass of a launch sequence, passed to the iteration kernels by value (constant bank).
+constexpr int kMaxPasses = 500;
+struct PassPtrs {
+    const uint4 *curBlk;
+    const uint32_t *refT;
+};
+struct PassTable {
+    PassPtrs p[kMaxPasses];
+};
+
+// Counters of the work lists (see ame_emit_kernel in ame_kernels.cu).
+struct WorkLists {
+    unsigned nSmall, nBig;          // entries
+    unsigned nextSmall, nextBig;    // tickets handed out by the running ame_iter_* launch
 };
 
 struct KParams {
     int W, H, ctuCols, nCtus, padStride;
-    size_t planeRecs;   // (padStride / 4) * (H + 2*kPad): 8-byte records per (copy, phase) plane
+    size_t planeWords;  // (padStride / 2) * (H + 2*kPad): words per phase plane
     int nPasses;
     int cvtRule, fusedBacksub, earlyExit;
     const PassDesc *passes;   // device array [nPasses]
-    const uint32_t *bigTab;   // device array [nBig] packed CU words
-    const uint2 *smallTab;    // device array [nSmall] (first, second) packed CU words
-    int nBig, nSmall;
     const uint32_t *slotTab;  // device array [kSlotsPerCtu]: packed CU word of every slot
+    CuState *state;           // [nPasses * nCtus * kSlotsPerCtu] search state, pass-major
+    CuAccum *accum;           // same indexing: SATD and moments of the iteration in flight
+    unsigned char *goFlag;    // same indexing: 1 = the CU takes part in the next iteration
+    uint2 *blockCnt, *blockOff;  // per 128-CU block of the state array: teams (one-warp, one-CTA) it contributes / their offsets
+    WorkLists *work;          // sizes and ticket counters of the lists
+    uint4 *smallList;         // capacity: one entry per CU
+    uint2 *bigList;
     int extraIter;            // --ExtraGradientIter of this batch (uniform per launch sequence)
 };
 
 // Launches the search kernels (ame_phase_kernel / ame_iter_kernel / ame_update_kernel, one iteration per launch)
-// for all passes on `stream`; returns launches made.
-int launch_search(const KParams &kp, cudaStream_t stream, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);
+// for all passes (at most kMaxPasses) on `stream`; returns launches made.
+int launch_search(const KParams &kp, const PassTable &pt, int numSMs, cudaStream_t stream, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);
 // dst (padded, stride padStride) <- edge-replicated src (W x H).
 void launch_pad(const uint16_t *src, uint16_t *dst, int W, int H, int padStride, cudaStream_t stream);
-// refT[4][16][H + 2*kPad][padStride/4] <- first interpolation stage of the padded plane `pad`, all 16 phases, in four
-// column alignments (8-byte records of four int16).
-void launch_phase_planes(const uint16_t *pad, uint2 *refT, int W, int H, int padStride, cudaStream_t stream);
+// refT[16][H + 2*kPad][padStride/2] <- first interpolation stage of the padded plane `pad`, all 16 phases (int16 pairs).
+void launch_phase_planes(const uint16_t *pad, uint32_t *refT, int W, int H, int padStride, cudaStream_t stream);
 // blk <- src (W x H) in 4x4-block order (32 bytes per block, (W/4) x ceil(H/4) blocks).
 void launch_block_plane(const uint16_t *src, uint4 *blk, int W, int H, cudaStream_t stream);
 
