@@ -109,7 +109,7 @@ int ame_upload_plane(ame_ctx *ctx, int slot, const uint16_t *plane);
 /* Same with an explicit role mask.  AME_ROLE_CURRENT: the plane will be searched FOR (original frames; kept a
  * second time in 4x4-block order); AME_ROLE_REFERENCE: the plane will be searched IN (reconstructed frames) -- this
  * runs the horizontal interpolation stage for all 16 phases once and keeps the result
- * (16 x (W+320) x (H+320) x 2 bytes of device memory, allocated on the slot's first reference upload).
+ * (2 x 16 x (W+320) x (H+320) x 2 bytes of device memory, allocated on the slot's first reference upload).
  * ame_upload_plane gives both roles; ame_search fails with AME_E_STATE on a slot that lacks the role it needs. */
 enum { AME_ROLE_CURRENT = 1, AME_ROLE_REFERENCE = 2 };
 int ame_upload_plane_ex(ame_ctx *ctx, int slot, const uint16_t *plane, int roles);

@@ -36,7 +36,7 @@ static int fail(int code, const char *fmt, ...) {
 struct Slot {
     uint16_t *raw = nullptr;    // W x H, as uploaded
     uint4 *blk = nullptr;       // current-frame role: the plane in 4x4-block order; allocated on first use
-    uint32_t *refT = nullptr;   // reference role: 16 pre-filtered planes; allocated on first use
+    uint4 *refT = nullptr;      // reference role: 2 x 16 pre-filtered planes; allocated on first use
     bool hasCur = false, hasRef = false;  // blk / refT match the current contents of raw
 };
 
@@ -76,7 +76,7 @@ struct ame_ctx {
     int lastLaunches = 0;
     uint16_t *padScratch = nullptr;  // (W + 2*kPad) x (H + 2*kPad) edge-replicated plane, input of the phase filter
     size_t planeElems = 0;  // samples of the padded plane
-    size_t planeWords = 0;  // words per phase plane of refT
+    size_t planeRecs = 0;   // 16-byte records per (copy, phase) plane of refT
     std::vector<Slot> slots;
     std::vector<ResultBlock> results;
     PassDesc *dPasses = nullptr;   // device [maxInFlight]
@@ -189,7 +189,7 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
     c->slots.resize(num_slots);
     const size_t rawBytes = (size_t)width * height * sizeof(uint16_t);
     c->planeElems = (size_t)c->padStride * (height + 2 * kPad);
-    c->planeWords = (size_t)(c->padStride / 2) * (height + 2 * kPad);
+    c->planeRecs = (size_t)(c->padStride / 8) * (height + 2 * kPad);
     CTX_TRY(cudaMalloc(&c->padScratch, c->planeElems * sizeof(uint16_t) + 64));
     for (Slot &s : c->slots) CTX_TRY(cudaMalloc(&s.raw, rawBytes));
     size_t off[8], total = 0;
@@ -271,7 +271,7 @@ int ame_upload_plane_ex(ame_ctx *c, int slot, const uint16_t *plane, int roles) 
     }
     if (roles & AME_ROLE_REFERENCE) {
         if (!s.refT) {
-            cudaError_t e = cudaMalloc(&s.refT, 16 * c->planeWords * sizeof(uint32_t));
+            cudaError_t e = cudaMalloc(&s.refT, 2 * 16 * c->planeRecs * sizeof(uint4));
             if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? AME_E_NOMEM : AME_E_CUDA, "pre-filtered planes of slot %d: %s", slot, cudaGetErrorString(e));
         }
         launch_pad(s.raw, c->padScratch, c->W, c->H, c->padStride, c->up);
@@ -350,7 +350,7 @@ int ame_flush(ame_ctx *c) {
     CU_TRY(cudaMemcpyAsync(c->dPasses + first, c->hPasses + first, sizeof(PassDesc) * n, cudaMemcpyHostToDevice, c->stream));
     KParams kp;
     kp.W = c->W; kp.H = c->H; kp.ctuCols = c->ctuCols; kp.nCtus = c->nCtus; kp.padStride = c->padStride;
-    kp.planeWords = c->planeWords;
+    kp.planeRecs = c->planeRecs;
     kp.cvtRule = c->cvtRule; kp.fusedBacksub = c->fusedBacksub; kp.earlyExit = c->earlyExit;
     kp.slotTab = c->dSlotTab; kp.extraIter = c->queuedExtra;
     kp.state = c->dState; kp.accum = c->dAccum;

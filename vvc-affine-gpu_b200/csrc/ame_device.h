@@ -32,8 +32,8 @@ struct CuAccum {
 // One queued search, as the kernels see it.
 struct PassDesc {
     const uint4 *curBlk;     // current plane in 4x4-block order (launch_block_plane): 2 x uint4 per block
-    const uint32_t *refT;    // first-stage rows of the reference (launch_phase_planes): 16 phase planes of
-                             // (H + 2*kPad) rows x padStride/2 words of two int16, (0,0) of the frame at sample [kPad][kPad]
+    const uint4 *refT;       // first-stage rows of the reference (launch_phase_planes): [2 copies][16 phases] planes of
+                             // (H + 2*kPad) rows x padStride/8 records of eight int16, (0,0) of the frame at sample [kPad][kPad]
     long long *cost[4];
     ame_cpmvs *cpmvs[4];
     float lambda;
@@ -44,7 +44,7 @@ struct PassDesc {
 constexpr int kMaxPasses = 500;
 struct PassPtrs {
     const uint4 *curBlk;
-    const uint32_t *refT;
+    const uint4 *refT;
 };
 struct PassTable {
     PassPtrs p[kMaxPasses];
@@ -58,7 +58,7 @@ struct WorkLists {
 
 struct KParams {
     int W, H, ctuCols, nCtus, padStride;
-    size_t planeWords;  // (padStride / 2) * (H + 2*kPad): words per phase plane
+    size_t planeRecs;   // (padStride / 8) * (H + 2*kPad): 16-byte records per (copy, phase) plane
     int nPasses;
     int cvtRule, fusedBacksub, earlyExit;
     const PassDesc *passes;   // device array [nPasses]
@@ -78,8 +78,9 @@ struct KParams {
 int launch_search(const KParams &kp, const PassTable &pt, int numSMs, cudaStream_t stream, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);
 // dst (padded, stride padStride) <- edge-replicated src (W x H).
 void launch_pad(const uint16_t *src, uint16_t *dst, int W, int H, int padStride, cudaStream_t stream);
-// refT[16][H + 2*kPad][padStride/2] <- first interpolation stage of the padded plane `pad`, all 16 phases (int16 pairs).
-void launch_phase_planes(const uint16_t *pad, uint32_t *refT, int W, int H, int padStride, cudaStream_t stream);
+// refT[2][16][H + 2*kPad][padStride/8] <- first interpolation stage of the padded plane `pad`, all 16 phases, int16, in
+// 16-byte records; the second copy is shifted by four columns.
+void launch_phase_planes(const uint16_t *pad, uint4 *refT, int W, int H, int padStride, cudaStream_t stream);
 // blk <- src (W x H) in 4x4-block order (32 bytes per block, (W/4) x ceil(H/4) blocks).
 void launch_block_plane(const uint16_t *src, uint4 *blk, int W, int H, cudaStream_t stream);
 
