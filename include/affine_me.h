@@ -82,8 +82,11 @@ enum {
                                   0 = x86 cvttsd2si (what it does on a CPU OpenCL device) */
     AME_OPT_FUSED_BACKSUB = 2, /* 1 (default) = back-substitution accumulates with FMA, as OpenCL's
                                   default FP_CONTRACT ON compiles affine.cl:851 */
-    AME_OPT_EARLY_EXIT = 3     /* 1 (default) = stop a CU's refinement once its CPMVs revisit an
+    AME_OPT_EARLY_EXIT = 3,    /* 1 (default) = stop a CU's refinement once its CPMVs revisit an
                                   already evaluated state (results are identical either way) */
+    AME_OPT_REUSE_START = 4    /* 1 (default) = a 3-CP search whose start state moves every sub-block exactly like the best
+                                  2-CP state reuses that state's SATD and normal equations instead of evaluating it again
+                                  (results are identical either way) */
 };
 
 typedef struct ame_ctx ame_ctx;

@@ -124,6 +124,26 @@ def test_early_exit_is_exact(pkg):
     assert _diff(out[0][0], out[0][1], out[1][0], out[1][1]) == 0
 
 
+def test_reuse_start_is_exact(pkg):
+    """AME_OPT_REUSE_START: skipping the first 3-CP evaluation where its motion field equals the best 2-CP state's
+    must not change any decision (with and without extra iterations, which move the best state around)."""
+    orig, recon = sf.sequences(2, 832, 480, 27, seed=sf.SEED + 57)
+    lam = ob.lambda_for(27, 2)
+    for extra in (0, 2):
+        out = []
+        for reuse in (1, 0):
+            ctx = pkg.AffineME(832, 480)
+            try:
+                ctx.set_option(pkg.OPT_REUSE_START, reuse)
+                out.append(ctx.ref_pass(recon[0], orig[1], lam, extra))
+            finally:
+                ctx.close()
+        assert _diff(out[0][0], out[0][1], out[1][0], out[1][1]) == 0
+        if extra == 0:
+            oc, om = ob.ref_pass(recon[0], orig[1], lam)
+            assert _diff(out[0][0], out[0][1], oc, om) == 0
+
+
 def test_1080p_properties(pkg):
     """Full-size checks: batched == one-by-one, run-to-run determinism, the fixed rows of out-of-frame CUs, and
     CTU row 0 against the oracle run on a 1920x256 strip (row 0's searches never reach the strip's bottom edge,

@@ -55,18 +55,19 @@ struct Pending {
 struct ame_ctx {
     int device = 0, W = 0, H = 0, nCtus = 0, ctuCols = 0, padStride = 0;
     int numSlots = 0, maxInFlight = 0;
-    int cvtRule = 1, fusedBacksub = 1, earlyExit = 1;
+    int cvtRule = 1, fusedBacksub = 1, earlyExit = 1, reuseStart = 1;
     int queuedExtra = 0;
     int numSMs = 0;
     uint32_t *dSlotTab = nullptr;
     // scratch of a launch sequence (ame_device.h): search state, accumulators and work lists for maxInFlight passes
     CuState *dState = nullptr;
     CuAccum *dAccum = nullptr;
+    size_t seqSlots = 0;
     unsigned char *dGoFlag = nullptr;
-    uint2 *dBlockCnt = nullptr, *dBlockOff = nullptr;
+    uint4 *dBlockCnt = nullptr, *dBlockOff = nullptr;
     WorkLists *dWork = nullptr;
     uint4 *dSmallList = nullptr;
-    uint2 *dBigList = nullptr;
+    uint2 *dBigList = nullptr, *dUpdList = nullptr;
     cudaStream_t stream = nullptr, side = nullptr;  // search kernels (big CUs / small CUs)
     cudaStream_t up = nullptr, down = nullptr;      // plane uploads + preparation / result copies
     cudaEvent_t evUp = nullptr, evKernels = nullptr, evAux = nullptr;
@@ -122,6 +123,7 @@ void ame_destroy(ame_ctx *c) {
     cudaFree(c->dPasses);
     cudaFree(c->dState);
     cudaFree(c->dAccum);
+    cudaFree(c->dUpdList);
     cudaFree(c->dWork);
     cudaFree(c->dGoFlag);
     cudaFree(c->dBlockCnt);
@@ -207,11 +209,13 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
         const size_t seqPasses = (size_t)(max_in_flight < kMaxPasses ? max_in_flight : kMaxPasses);
         const size_t nSlots = seqPasses * c->nCtus * kSlotsPerCtu;
         CTX_TRY(cudaMalloc(&c->dState, nSlots * sizeof(CuState)));
-        CTX_TRY(cudaMalloc(&c->dAccum, nSlots * sizeof(CuAccum)));
+        c->seqSlots = nSlots;
+        CTX_TRY(cudaMalloc(&c->dAccum, 2 * nSlots * sizeof(CuAccum)));
+        CTX_TRY(cudaMalloc(&c->dUpdList, nSlots * sizeof(uint2)));
         CTX_TRY(cudaMalloc(&c->dWork, sizeof(WorkLists)));
         CTX_TRY(cudaMalloc(&c->dGoFlag, nSlots));
-        CTX_TRY(cudaMalloc(&c->dBlockCnt, ((nSlots + 127) / 128) * sizeof(uint2)));
-        CTX_TRY(cudaMalloc(&c->dBlockOff, ((nSlots + 127) / 128) * sizeof(uint2)));
+        CTX_TRY(cudaMalloc(&c->dBlockCnt, ((nSlots + 127) / 128) * sizeof(uint4)));
+        CTX_TRY(cudaMalloc(&c->dBlockOff, ((nSlots + 127) / 128) * sizeof(uint4)));
         CTX_TRY(cudaMalloc(&c->dSmallList, nSlots * sizeof(uint4)));
         CTX_TRY(cudaMalloc(&c->dBigList, seqPasses * c->nCtus * 9 * sizeof(uint2)));
     }
@@ -240,6 +244,7 @@ int ame_set_option(ame_ctx *c, int option, int value) {
         case AME_OPT_CVT_RULE: c->cvtRule = value ? 1 : 0; return AME_OK;
         case AME_OPT_FUSED_BACKSUB: c->fusedBacksub = value ? 1 : 0; return AME_OK;
         case AME_OPT_EARLY_EXIT: c->earlyExit = value ? 1 : 0; return AME_OK;
+        case AME_OPT_REUSE_START: c->reuseStart = value ? 1 : 0; return AME_OK;
     }
     return fail(AME_E_INVALID, "ame_set_option: unknown option %d", option);
 }
@@ -353,7 +358,8 @@ int ame_flush(ame_ctx *c) {
     kp.planeRecs = c->planeRecs;
     kp.cvtRule = c->cvtRule; kp.fusedBacksub = c->fusedBacksub; kp.earlyExit = c->earlyExit;
     kp.slotTab = c->dSlotTab; kp.extraIter = c->queuedExtra;
-    kp.state = c->dState; kp.accum = c->dAccum;
+    kp.state = c->dState; kp.accum = c->dAccum; kp.accumStride = (unsigned)c->seqSlots; kp.updList = c->dUpdList;
+    kp.reuseStart = c->reuseStart;
     kp.goFlag = c->dGoFlag; kp.blockCnt = c->dBlockCnt; kp.blockOff = c->dBlockOff;
     kp.work = c->dWork; kp.smallList = c->dSmallList; kp.bigList = c->dBigList;
     CU_TRY(cudaStreamWaitEvent(c->stream, c->evUp, 0));  // every plane uploaded so far is ready (no-op if none)

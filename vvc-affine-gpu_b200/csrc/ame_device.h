@@ -22,7 +22,7 @@ struct CuState {
     int best[6];
     long long bestCost;
     int h1[6], h2[6];    // the two states evaluated before cur
-    int done, pad;
+    int hasMom, wbuf;    // wbuf: accumulator (0 / 1) the next evaluation writes; hasMom: accumulator wbuf ^ 1 belongs to `best`
 };
 struct CuAccum {
     long long mom[24];   // moments of the normal equations (numbering of kMomOf in ame_kernels.cu)
@@ -52,8 +52,8 @@ struct PassTable {
 
 // Counters of the work lists (see ame_emit_kernel in ame_kernels.cu).
 struct WorkLists {
-    unsigned nSmall, nBig;          // entries
-    unsigned nextSmall, nextBig;    // tickets handed out by the running ame_iter_* launch
+    unsigned nSmall, nBig, nUpd;    // entries
+    unsigned nextSmall, nextBig, pad[3];  // tickets handed out by the running ame_iter_* launch
 };
 
 struct KParams {
@@ -64,12 +64,15 @@ struct KParams {
     const PassDesc *passes;   // device array [nPasses]
     const uint32_t *slotTab;  // device array [kSlotsPerCtu]: packed CU word of every slot
     CuState *state;           // [nPasses * nCtus * kSlotsPerCtu] search state, pass-major
-    CuAccum *accum;           // same indexing: SATD and moments of the iteration in flight
-    unsigned char *goFlag;    // same indexing: 1 = the CU takes part in the next iteration
-    uint2 *blockCnt, *blockOff;  // per 128-CU block of the state array: teams (one-warp, one-CTA) it contributes / their offsets
+    CuAccum *accum;           // [2][accumStride], same indexing: SATD and moments of the iteration in flight / of the best state
+    unsigned accumStride;
+    unsigned char *goFlag;    // same indexing: 1 = the CU is evaluated by the next iteration, 2 = it only takes part in the update
+    uint4 *blockCnt, *blockOff;  // per 128-CU block of the state array: teams (one-warp, one-CTA, update-only) it contributes / offsets
     WorkLists *work;          // sizes and ticket counters of the lists
     uint4 *smallList;         // capacity: one entry per CU
     uint2 *bigList;
+    uint2 *updList;           // CUs that skip the evaluation of the next iteration
+    int reuseStart;           // 1: the 3-CP search reuses the evaluation of the best 2-CP state where the motion fields agree
     int extraIter;            // --ExtraGradientIter of this batch (uniform per launch sequence)
 };
 
