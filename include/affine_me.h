@@ -84,8 +84,11 @@ enum {
                                   default FP_CONTRACT ON compiles affine.cl:851 */
     AME_OPT_EARLY_EXIT = 3,    /* 1 (default) = stop a CU's refinement once its CPMVs revisit an
                                   already evaluated state (results are identical either way) */
-    AME_OPT_REUSE_START = 4    /* 1 (default) = a 3-CP search whose start state moves every sub-block exactly like the best
+    AME_OPT_REUSE_START = 4,   /* 1 (default) = a 3-CP search whose start state moves every sub-block exactly like the best
                                   2-CP state reuses that state's SATD and normal equations instead of evaluating it again
+                                  (results are identical either way) */
+    AME_OPT_SHARE_FIRST = 5    /* 1 (default) = the first evaluation of the 2-CP searches (zero motion for every CU) is
+                                  computed once per 4x4 block and summed per CU instead of once per CU
                                   (results are identical either way) */
 };
 

@@ -144,6 +144,25 @@ def test_reuse_start_is_exact(pkg):
             assert _diff(out[0][0], out[0][1], oc, om) == 0
 
 
+def test_share_first_is_exact(pkg):
+    """AME_OPT_SHARE_FIRST: evaluating the zero-motion start of all 2-CP searches once per 4x4 block (nine border-ring
+    cases) and summing per CU must give the decisions of the per-CU evaluation; 416x240 has partial CTUs on both axes."""
+    for (W, H, seed) in ((832, 480, 61), (416, 240, 62)):
+        orig, recon = sf.sequences(1, W, H, 32, seed=sf.SEED + seed)
+        lam = ob.lambda_for(32, 1)
+        out = []
+        for share in (1, 0):
+            ctx = pkg.AffineME(W, H)
+            try:
+                ctx.set_option(pkg.OPT_SHARE_FIRST, share)
+                out.append(ctx.ref_pass(recon[0], orig[0], lam))
+            finally:
+                ctx.close()
+        assert _diff(out[0][0], out[0][1], out[1][0], out[1][1]) == 0
+        oc, om = ob.ref_pass(recon[0], orig[0], lam)
+        assert _diff(out[0][0], out[0][1], oc, om) == 0
+
+
 def test_1080p_properties(pkg):
     """Full-size checks: batched == one-by-one, run-to-run determinism, the fixed rows of out-of-frame CUs, and
     CTU row 0 against the oracle run on a 1920x256 strip (row 0's searches never reach the strip's bottom edge,

@@ -17,7 +17,7 @@ CLI_PATH = os.path.join(HERE, "bin", "affine_b200")
 PRED_NAMES = ("FULL_2CP", "FULL_3CP", "HALF_2CP", "HALF_3CP")
 CPMV_DTYPE = np.dtype([("nCPs", "<i4"), ("LTx", "<i4"), ("LTy", "<i4"), ("RTx", "<i4"),
                        ("RTy", "<i4"), ("LBx", "<i4"), ("LBy", "<i4")])
-OPT_CVT_RULE, OPT_FUSED_BACKSUB, OPT_EARLY_EXIT, OPT_REUSE_START = 1, 2, 3, 4
+OPT_CVT_RULE, OPT_FUSED_BACKSUB, OPT_EARLY_EXIT, OPT_REUSE_START, OPT_SHARE_FIRST = 1, 2, 3, 4, 5
 ROLE_CURRENT, ROLE_REFERENCE = 1, 2
 
 # every symbol include/affine_me.h declares

@@ -55,7 +55,7 @@ struct Pending {
 struct ame_ctx {
     int device = 0, W = 0, H = 0, nCtus = 0, ctuCols = 0, padStride = 0;
     int numSlots = 0, maxInFlight = 0;
-    int cvtRule = 1, fusedBacksub = 1, earlyExit = 1, reuseStart = 1;
+    int cvtRule = 1, fusedBacksub = 1, earlyExit = 1, reuseStart = 1, shareFirst = 1;
     int queuedExtra = 0;
     int numSMs = 0;
     uint32_t *dSlotTab = nullptr;
@@ -68,6 +68,7 @@ struct ame_ctx {
     WorkLists *dWork = nullptr;
     uint4 *dSmallList = nullptr;
     uint2 *dBigList = nullptr, *dUpdList = nullptr;
+    int *dTab0 = nullptr;
     cudaStream_t stream = nullptr, side = nullptr;  // search kernels (big CUs / small CUs)
     cudaStream_t up = nullptr, down = nullptr;      // plane uploads + preparation / result copies
     cudaEvent_t evUp = nullptr, evKernels = nullptr, evAux = nullptr;
@@ -124,6 +125,7 @@ void ame_destroy(ame_ctx *c) {
     cudaFree(c->dState);
     cudaFree(c->dAccum);
     cudaFree(c->dUpdList);
+    cudaFree(c->dTab0);
     cudaFree(c->dWork);
     cudaFree(c->dGoFlag);
     cudaFree(c->dBlockCnt);
@@ -212,6 +214,7 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
         c->seqSlots = nSlots;
         CTX_TRY(cudaMalloc(&c->dAccum, 2 * nSlots * sizeof(CuAccum)));
         CTX_TRY(cudaMalloc(&c->dUpdList, nSlots * sizeof(uint2)));
+        CTX_TRY(cudaMalloc(&c->dTab0, (size_t)2 * c->numSMs * (1024 * 45 + 1024) * sizeof(int)));
         CTX_TRY(cudaMalloc(&c->dWork, sizeof(WorkLists)));
         CTX_TRY(cudaMalloc(&c->dGoFlag, nSlots));
         CTX_TRY(cudaMalloc(&c->dBlockCnt, ((nSlots + 127) / 128) * sizeof(uint4)));
@@ -245,6 +248,7 @@ int ame_set_option(ame_ctx *c, int option, int value) {
         case AME_OPT_FUSED_BACKSUB: c->fusedBacksub = value ? 1 : 0; return AME_OK;
         case AME_OPT_EARLY_EXIT: c->earlyExit = value ? 1 : 0; return AME_OK;
         case AME_OPT_REUSE_START: c->reuseStart = value ? 1 : 0; return AME_OK;
+        case AME_OPT_SHARE_FIRST: c->shareFirst = value ? 1 : 0; return AME_OK;
     }
     return fail(AME_E_INVALID, "ame_set_option: unknown option %d", option);
 }
@@ -359,7 +363,7 @@ int ame_flush(ame_ctx *c) {
     kp.cvtRule = c->cvtRule; kp.fusedBacksub = c->fusedBacksub; kp.earlyExit = c->earlyExit;
     kp.slotTab = c->dSlotTab; kp.extraIter = c->queuedExtra;
     kp.state = c->dState; kp.accum = c->dAccum; kp.accumStride = (unsigned)c->seqSlots; kp.updList = c->dUpdList;
-    kp.reuseStart = c->reuseStart;
+    kp.reuseStart = c->reuseStart; kp.shareFirst = c->shareFirst; kp.tab0 = c->dTab0;
     kp.goFlag = c->dGoFlag; kp.blockCnt = c->dBlockCnt; kp.blockOff = c->dBlockOff;
     kp.work = c->dWork; kp.smallList = c->dSmallList; kp.bigList = c->dBigList;
     CU_TRY(cudaStreamWaitEvent(c->stream, c->evUp, 0));  // every plane uploaded so far is ready (no-op if none)
@@ -374,6 +378,7 @@ int ame_flush(ame_ctx *c) {
         for (int i = 0; i < m; i++) {
             pt.p[i].curBlk = c->hPasses[first + k0 + i].curBlk;
             pt.p[i].refT = c->hPasses[first + k0 + i].refT;
+            pt.p[i].refRaw = c->slots[c->queued[k0 + i].refSlot].raw;
         }
         c->lastLaunches += launch_search(kp, pt, c->numSMs, c->stream, c->side, c->evFork, c->evJoin);
     }

@@ -45,6 +45,7 @@ constexpr int kMaxPasses = 500;
 struct PassPtrs {
     const uint4 *curBlk;
     const uint4 *refT;
+    const uint16_t *refRaw;  // the reference plane as uploaded (W x H), for ame_iter0_kernel
 };
 struct PassTable {
     PassPtrs p[kMaxPasses];
@@ -72,6 +73,8 @@ struct KParams {
     uint4 *smallList;         // capacity: one entry per CU
     uint2 *bigList;
     uint2 *updList;           // CUs that skip the evaluation of the next iteration
+    int *tab0;                // scratch of ame_iter0_kernel: [2 * numSMs CTAs][1024 * 45 + 1024]
+    int shareFirst;           // 1: the first evaluation of all 2-CP searches is shared per sub-block (ame_iter0_kernel)
     int reuseStart;           // 1: the 3-CP search reuses the evaluation of the best 2-CP state where the motion fields agree
     int extraIter;            // --ExtraGradientIter of this batch (uniform per launch sequence)
 };
