@@ -217,6 +217,36 @@ def test_1080p_properties(pkg):
         assert (a == b).all()
 
 
+def test_many_searches_in_one_flush(pkg):
+    """More queued searches than one launch sequence holds (kMaxPasses = 500): the batch is cut into sequences that
+    share the scratch arrays; every search must still give the single-search result.  Also: role checks of slots."""
+    W, H = 416, 240
+    orig, recon = sf.sequences(2, W, H, 32, seed=sf.SEED + 71)
+    lam = [ob.lambda_for(32, 1), ob.lambda_for(32, 2)]
+    n = 520
+    ctx = pkg.AffineME(W, H, num_slots=4, max_in_flight=n)
+    try:
+        single = [ctx.ref_pass(recon[0], orig[0], lam[0]), ctx.ref_pass(recon[1], orig[1], lam[1])]
+        ctx.upload(0, orig[0], pkg.ROLE_CURRENT); ctx.upload(1, orig[1], pkg.ROLE_CURRENT)
+        ctx.upload(2, recon[0], pkg.ROLE_REFERENCE); ctx.upload(3, recon[1], pkg.ROLE_REFERENCE)
+        checked = (0, 1, 250, 499, 500, 501, 518, 519)
+        res = {k: pkg.HostResult(ctx) for k in checked}
+        dummy = pkg.HostResult(ctx)                      # destination of the searches that are not looked at
+        for k in range(n):
+            ctx.search(k & 1, 2 + (k & 1), lam[k & 1], res.get(k, dummy))
+        ctx.sync()
+        for k in checked:
+            assert _diff(res[k].cost, res[k].cpmvs, single[k & 1][0], single[k & 1][1]) == 0, k
+        with pytest.raises(pkg.AmeError, match="role"):
+            ctx.search(2, 3, lam[0], dummy)              # slot 2 holds no current-frame copy
+        with pytest.raises(pkg.AmeError, match="role"):
+            ctx.search(0, 1, lam[0], dummy)              # slot 1 holds no reference copy
+        for r in list(res.values()) + [dummy]:
+            r.free()
+    finally:
+        ctx.close()
+
+
 def test_error_behaviour(pkg):
     ctx = pkg.AffineME(416, 240, num_slots=2, max_in_flight=1)
     try:
