@@ -15,7 +15,7 @@ txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture
 lines, cur, infn = [], None, False
 for ln in txt.split("\n"):
     if ln.startswith(".text."):
-        infn = "ame_iter0_kernel" in ln
+        infn = "ame_update_kernel" in ln
     m = re.search(r'//## File "(.*?)", line (\d+)', ln)
     if m:
         cur = int(m.group(2)) if os.path.basename(m.group(1)) == os.path.basename(src_path) else -1
