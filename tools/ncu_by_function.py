@@ -1,9 +1,11 @@
 """Joins an ncu report's per-SASS-instruction counters with nvdisasm line info of the same kernel build and
-prints dynamic instruction counts / stall samples per source function.  usage: ncu_by_function.py report.ncu-rep [kernel#]"""
+prints dynamic instruction counts / stall samples per source function.
+usage: ncu_by_function.py report.ncu-rep [kernel# in the report] [kernel function name, default ame_iter_small]"""
 import bisect, collections, csv, io, os, re, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
-which = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+which = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+kname = sys.argv[3] if len(sys.argv) > 3 else "ame_iter_small"
 src_path = os.environ.get("AME_SRC") or os.path.join(ROOT, "vvc-affine-gpu_b200", "csrc", "ame_kernels.cu")
 tmp = tempfile.mkdtemp()
 obj = os.path.join(tmp, "k.o")
@@ -15,7 +17,7 @@ txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture
 lines, cur, infn = [], None, False
 for ln in txt.split("\n"):
     if ln.startswith(".text."):
-        infn = "ame_update_kernel" in ln
+        infn = kname in ln
     m = re.search(r'//## File "(.*?)", line (\d+)', ln)
     if m:
         cur = int(m.group(2)) if os.path.basename(m.group(1)) == os.path.basename(src_path) else -1
