@@ -124,6 +124,18 @@ def test_early_exit_is_exact(pkg):
     assert _diff(out[0][0], out[0][1], out[1][0], out[1][1]) == 0
 
 
+def test_shared_divisor_division(pkg):
+    """The update kernel divides a row by its pivot with the reciprocal refinement done once per pivot (div_prepare /
+    div_shared in ame_kernels.cu).  Every quotient must be the bits __ddiv_rn returns: arbitrary bit patterns, int64-derived
+    operands as the elimination sees them, and operands around the thresholds of the fast path."""
+    import ctypes
+    L = pkg.lib()
+    bad = ctypes.c_ulonglong(123)
+    rc = L.ame_debug_div_check(ctypes.c_ulonglong(1 << 26), ctypes.c_ulonglong(0xA11F1E5), ctypes.byref(bad))
+    assert rc == 0, L.ame_last_error()
+    assert bad.value == 0
+
+
 def test_reuse_start_is_exact(pkg):
     """AME_OPT_REUSE_START: skipping the first 3-CP evaluation where its motion field equals the best 2-CP state's
     must not change any decision (with and without extra iterations, which move the best state around)."""

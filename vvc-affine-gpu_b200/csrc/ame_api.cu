@@ -214,7 +214,7 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
         c->seqSlots = nSlots;
         CTX_TRY(cudaMalloc(&c->dAccum, 2 * nSlots * sizeof(CuAccum)));
         CTX_TRY(cudaMalloc(&c->dUpdList, nSlots * sizeof(uint2)));
-        CTX_TRY(cudaMalloc(&c->dTab0, (size_t)2 * c->numSMs * (1024 * 45 + 1024) * sizeof(int)));
+        CTX_TRY(cudaMalloc(&c->dTab0, (size_t)kIter0MaxCtas * c->numSMs * (1024 * 45 + 1024) * sizeof(int)));
         CTX_TRY(cudaMalloc(&c->dWork, sizeof(WorkLists)));
         CTX_TRY(cudaMalloc(&c->dGoFlag, nSlots));
         CTX_TRY(cudaMalloc(&c->dBlockCnt, ((nSlots + 127) / 128) * sizeof(uint4)));
@@ -450,6 +450,11 @@ int ame_timer_stop(ame_ctx *c, float *ms) {
 int ame_debug_stats(unsigned long long *out24, int reset) {
     debug_stats(out24, reset != 0);
     return AME_OK;
+}
+
+int ame_debug_div_check(unsigned long long n, unsigned long long seed, unsigned long long *mismatches) {
+    if (!mismatches) return fail(AME_E_INVALID, "ame_debug_div_check: NULL argument");
+    return debug_div_check(n, seed, mismatches) ? fail(AME_E_CUDA, "ame_debug_div_check: CUDA error") : AME_OK;
 }
 
 }  // extern "C"

@@ -57,6 +57,8 @@ struct WorkLists {
     unsigned nextSmall, nextBig, pad[3];  // tickets handed out by the running ame_iter_* launch
 };
 
+constexpr int kIter0MaxCtas = 4;  // resident CTAs per SM ame_iter0_kernel may be built for (AME_ITER0_CTAS)
+
 struct KParams {
     int W, H, ctuCols, nCtus, padStride;
     size_t planeRecs;   // (padStride / 8) * (H + 2*kPad): 16-byte records per (copy, phase) plane
@@ -73,7 +75,7 @@ struct KParams {
     uint4 *smallList;         // capacity: one entry per CU
     uint2 *bigList;
     uint2 *updList;           // CUs that skip the evaluation of the next iteration
-    int *tab0;                // scratch of ame_iter0_kernel: [2 * numSMs CTAs][1024 * 45 + 1024]
+    int *tab0;                // scratch of ame_iter0_kernel: [kIter0MaxCtas * numSMs CTAs][1024 * 45 + 1024]
     int shareFirst;           // 1: the first evaluation of all 2-CP searches is shared per sub-block (ame_iter0_kernel)
     int reuseStart;           // 1: the 3-CP search reuses the evaluation of the best 2-CP state where the motion fields agree
     int extraIter;            // --ExtraGradientIter of this batch (uniform per launch sequence)
@@ -92,5 +94,8 @@ void launch_block_plane(const uint16_t *src, uint4 *blk, int W, int H, cudaStrea
 
 // Development counters of builds with -DAME_STATS (zeros otherwise).
 void debug_stats(unsigned long long *out24, bool reset);
+
+// Development check of the shared-divisor division of the update kernel against __ddiv_rn (see ame_kernels.cu).
+int debug_div_check(unsigned long long n, unsigned long long seed, unsigned long long *mismatches);
 
 }  // namespace ame
