@@ -78,7 +78,7 @@ struct ame_ctx {
     int lastLaunches = 0;
     uint16_t *padScratch = nullptr;  // (W + 2*kPad) x (H + 2*kPad) edge-replicated plane, input of the phase filter
     size_t planeElems = 0;  // samples of the padded plane
-    size_t planeRecs = 0;   // 16-byte records per (copy, phase) plane of refT
+    size_t planeSetRecs = 0;  // 16-byte records of the 2 x 16 tiled pre-filtered planes of one reference (refT)
     std::vector<Slot> slots;
     std::vector<ResultBlock> results;
     PassDesc *dPasses = nullptr;   // device [maxInFlight]
@@ -193,7 +193,7 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
     c->slots.resize(num_slots);
     const size_t rawBytes = (size_t)width * height * sizeof(uint16_t);
     c->planeElems = (size_t)c->padStride * (height + 2 * kPad);
-    c->planeRecs = (size_t)(c->padStride / 8) * (height + 2 * kPad);
+    c->planeSetRecs = tiled_plane_set_recs(c->padStride, height + 2 * kPad);
     CTX_TRY(cudaMalloc(&c->padScratch, c->planeElems * sizeof(uint16_t) + 64));
     for (Slot &s : c->slots) CTX_TRY(cudaMalloc(&s.raw, rawBytes));
     size_t off[8], total = 0;
@@ -280,7 +280,7 @@ int ame_upload_plane_ex(ame_ctx *c, int slot, const uint16_t *plane, int roles) 
     }
     if (roles & AME_ROLE_REFERENCE) {
         if (!s.refT) {
-            cudaError_t e = cudaMalloc(&s.refT, 2 * 16 * c->planeRecs * sizeof(uint4));
+            cudaError_t e = cudaMalloc(&s.refT, c->planeSetRecs * sizeof(uint4));
             if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? AME_E_NOMEM : AME_E_CUDA, "pre-filtered planes of slot %d: %s", slot, cudaGetErrorString(e));
         }
         launch_pad(s.raw, c->padScratch, c->W, c->H, c->padStride, c->up);
@@ -359,7 +359,7 @@ int ame_flush(ame_ctx *c) {
     CU_TRY(cudaMemcpyAsync(c->dPasses + first, c->hPasses + first, sizeof(PassDesc) * n, cudaMemcpyHostToDevice, c->stream));
     KParams kp;
     kp.W = c->W; kp.H = c->H; kp.ctuCols = c->ctuCols; kp.nCtus = c->nCtus; kp.padStride = c->padStride;
-    kp.planeRecs = c->planeRecs;
+    kp.nStrips = tile_strips(c->padStride);
     kp.cvtRule = c->cvtRule; kp.fusedBacksub = c->fusedBacksub; kp.earlyExit = c->earlyExit;
     kp.slotTab = c->dSlotTab; kp.extraIter = c->queuedExtra;
     kp.state = c->dState; kp.accum = c->dAccum; kp.accumStride = (unsigned)c->seqSlots; kp.updList = c->dUpdList;

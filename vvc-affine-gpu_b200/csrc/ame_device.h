@@ -14,6 +14,24 @@ namespace ame {
 // the worst case; 160 keeps rows 64-byte aligned.
 constexpr int kPad = 160;
 
+// Tiled layout of the 2 x 16 pre-filtered planes of a reference (PassDesc::refT).  A tile = 128 rows (+ 8 rows
+// repeated from the next tile, so that the nine rows of a sub-block window never leave the tile of their first row) x
+// one 64-column strip (8 records = one 128-byte line per row); the 32 planes of a tile are adjacent.  What the CUs
+// of a CTU touch under all phases is then a few contiguous 0.5 MB pieces instead of 32 x 170 row segments that lie a
+// plane row (4..16 KB) apart: the same DRAM bytes, but a handful of pages for the TLBs.  Within a tile, consecutive
+// rows are 8 records apart whatever the frame width (immediate offsets for the nine loads of a window).
+constexpr int kTileRows = 128, kTileHalo = 8;
+constexpr int kTileRecs = (kTileRows + kTileHalo) * 8;  // records of one plane of one tile
+__host__ __device__ inline int tile_strips(int padStride) { return (padStride + 63) >> 6; }
+__host__ __device__ inline int tile_row_blocks(int padRows) { return (padRows + kTileRows - 1) / kTileRows; }
+// record index of (plane, row, record column) for a window whose FIRST row is `row` (or for row itself)
+__host__ __device__ inline unsigned tile_record(int nStrips, int plane, int row, int rec) {
+    return (unsigned)(((row >> 7) * nStrips + (rec >> 3)) * 32 + plane) * (unsigned)kTileRecs + (unsigned)((row & 127) * 8 + (rec & 7));
+}
+__host__ __device__ inline size_t tiled_plane_set_recs(int padStride, int padRows) {
+    return (size_t)tile_row_blocks(padRows) * tile_strips(padStride) * 32 * kTileRecs;
+}
+
 // Per-CU search state and per-iteration accumulators (ame_iter_kernel / ame_update_kernel).
 // Slot k of a CTU: aligned CUs 0..200 (result index), half-aligned CUs 201..484.
 constexpr int kSlotsPerCtu = AME_ALIGNED_CUS_PER_CTU + AME_HALF_CUS_PER_CTU;
@@ -32,8 +50,9 @@ struct CuAccum {
 // One queued search, as the kernels see it.
 struct PassDesc {
     const uint4 *curBlk;     // current plane in 4x4-block order (launch_block_plane): 2 x uint4 per block
-    const uint4 *refT;       // first-stage rows of the reference (launch_phase_planes): [2 copies][16 phases] planes of
-                             // (H + 2*kPad) rows x padStride/8 records of eight int16, (0,0) of the frame at sample [kPad][kPad]
+    const uint4 *refT;       // first-stage rows of the reference (launch_phase_planes): 2 copies x 16 phases of
+                             // (H + 2*kPad) rows x padStride/8 records of eight int16, (0,0) of the frame at sample
+                             // [kPad][kPad], stored in tiles (see tile_record)
     long long *cost[4];
     ame_cpmvs *cpmvs[4];
     float lambda;
@@ -61,7 +80,7 @@ constexpr int kIter0MaxCtas = 4;  // resident CTAs per SM ame_iter0_kernel may b
 
 struct KParams {
     int W, H, ctuCols, nCtus, padStride;
-    size_t planeRecs;   // (padStride / 8) * (H + 2*kPad): 16-byte records per (copy, phase) plane
+    int nStrips;        // 64-column strips per row of the pre-filtered planes (tile_record)
     int nPasses;
     int cvtRule, fusedBacksub, earlyExit;
     const PassDesc *passes;   // device array [nPasses]
@@ -86,8 +105,8 @@ struct KParams {
 int launch_search(const KParams &kp, const PassTable &pt, int numSMs, cudaStream_t stream, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);
 // dst (padded, stride padStride) <- edge-replicated src (W x H).
 void launch_pad(const uint16_t *src, uint16_t *dst, int W, int H, int padStride, cudaStream_t stream);
-// refT[2][16][H + 2*kPad][padStride/8] <- first interpolation stage of the padded plane `pad`, all 16 phases, int16, in
-// 16-byte records; the second copy is shifted by four columns.
+// refT (tiled, tile_record) <- first interpolation stage of the padded plane `pad`, all 16 phases, int16, in
+// 16-byte records; the second copy (planes 16..31) is shifted by four columns.
 void launch_phase_planes(const uint16_t *pad, uint4 *refT, int W, int H, int padStride, cudaStream_t stream);
 // blk <- src (W x H) in 4x4-block order (32 bytes per block, (W/4) x ceil(H/4) blocks).
 void launch_block_plane(const uint16_t *src, uint4 *blk, int W, int H, cudaStream_t stream);
