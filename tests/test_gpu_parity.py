@@ -56,7 +56,10 @@ def test_cuda_matches_reference_logs(pkg, path):
         ctx.close()
 
 
-@pytest.mark.parametrize("W,H,seed,qp", [(416, 240, 11, 27), (416, 240, 12, 37), (832, 480, 13, 32), (1280, 720, 14, 22)])
+# (424 x 236 and 1000 x 600: padded widths that are not a multiple of the 32-column tile strips, heights that are not a
+# multiple of 4 / 128)
+@pytest.mark.parametrize("W,H,seed,qp", [(416, 240, 11, 27), (416, 240, 12, 37), (832, 480, 13, 32), (1280, 720, 14, 22),
+                                         (424, 236, 15, 32), (1000, 600, 16, 27)])
 def test_cuda_matches_oracle_on_seeded_inputs(pkg, W, H, seed, qp):
     orig, recon = sf.sequences(1, W, H, qp, seed=sf.SEED + seed)
     lam = ob.lambda_for(qp, 1)
@@ -227,6 +230,26 @@ def test_1080p_properties(pkg):
         a = single[0][0][pred].reshape(135, per)[:15]
         b = oc[pred].reshape(30, per)[:15]
         assert (a == b).all()
+
+
+def test_second_device_in_the_same_process(pkg):
+    """The CLI's --NumDevices path drives several GPUs from one process: everything that is per-device state (kernel
+    attributes, streams, scratch) must be set up for each of them.  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    orig, recon = sf.sequences(1, 416, 240, 32, seed=sf.SEED + 5)
+    lam = ob.lambda_for(32, 1)
+    out = []
+    for dev in (0, 1):
+        ctx = pkg.AffineME(416, 240, device=dev)
+        try:
+            out.append(ctx.ref_pass(recon[0], orig[0], lam))
+        finally:
+            ctx.close()
+    assert _diff(out[0][0], out[0][1], out[1][0], out[1][1]) == 0
+    oc, om = ob.ref_pass(recon[0], orig[0], lam)
+    assert _diff(out[1][0], out[1][1], oc, om) == 0
 
 
 def test_many_searches_in_one_flush(pkg):
