@@ -350,6 +350,10 @@ def run_b200(args, rank, world, local_rank):
                                  "bytes/pass = %d (%.1f GB/s, vs %.0f GB/s measured HBM peak)" % (
                                      OPS_PER_PASS / 1e9, sm_mhz, ALGO_BYTES_PER_PASS, ALGO_BYTES_PER_PASS * per_gpu_passes / 1e9,
                                      peaks.get("hbm_gbs", 6650.0)),
+                         "frac_note": "the op model counts the work as the reference writes it; the exact shortcuts (early exit on a "
+                                      "revisited state, shared first 2-CP evaluation, 3-CP start reuse) skip part of it, so frac can "
+                                      "exceed 1 -- ncu_issue_active_pct is the hardware-side figure of the dominant kernel",
+                         "ncu_issue_active_pct": ncu_issue_active(),
                          "kernel_ms_per_step": kernel_ms},
             "cpu_baseline": {"value": cb_fps, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": "one full 1080p reference pass (poc 1, ref 0, QP 32), %.1f s" % cb_dt,
@@ -359,6 +363,17 @@ def run_b200(args, rank, world, local_rank):
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def ncu_issue_active():
+    """smsp__issue_active of ame_iter_small (60 % of the step) from the committed ncu --set full capture, or None."""
+    try:
+        for ln in open(os.path.join(ROOT, "profiles", "r01_final_ncu_ame_iter_small.txt")):
+            if ln.startswith("smsp__issue_active.avg.pct_of_peak_sustained_active"):
+                return float(ln.split()[-1])
+    except OSError:
+        pass
+    return None
 
 
 def main():
