@@ -152,6 +152,8 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
     *out = nullptr;
     if (width < 16 || height < 16 || (width % 8) != 0) return fail(AME_E_INVALID, "ame_create: unsupported size %dx%d (width must be a multiple of 8, both >= 16)", width, height);
     if (num_slots < 2 || max_in_flight < 1) return fail(AME_E_INVALID, "ame_create: need num_slots >= 2 and max_in_flight >= 1");
+    if (tiled_plane_set_recs(width + 2 * kPad, height + 2 * kPad) > 0xffffffffull || (long long)ame_num_ctus(width, height) > 0xffff)
+        return fail(AME_E_INVALID, "ame_create: %dx%d is beyond the 32-bit record index of the pre-filtered planes / 16-bit CTU index of the work lists", width, height);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) return fail(AME_E_CUDA, "ame_create: no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
