@@ -265,7 +265,11 @@ def run_b200(args, rank, world, local_rank):
         barrier()
         return ms
 
-    CHUNK = 8  # frames per launch in the end-to-end path: uploads of chunk k+1 overlap the kernels of chunk k
+    # frames per launch sequence in the end-to-end path: uploads of chunk k+1 and result copies of chunk k-1 overlap
+    # the kernels of chunk k; the first upload and the last copy overlap nothing, so the first and last chunks are short
+    CHUNK = 8
+    CHUNKS = [int(x) for x in os.environ.get("AME_BENCH_CHUNKS", "").split(",") if x] or [2, 6] + [CHUNK] * ((N_FRAMES - 16) // CHUNK) + [6, 2]
+    assert sum(CHUNKS) == N_FRAMES
 
     def step_e2e(step):
         qp = QPS[step % 4]
@@ -273,11 +277,13 @@ def run_b200(args, rank, world, local_rank):
         t0 = time.perf_counter()
         ctx.timer_start()
         k = 0
-        for f0 in range(0, N_FRAMES, CHUNK):
-            for f in range(f0, min(N_FRAMES, f0 + CHUNK)):
+        f0 = 0
+        for chunk in CHUNKS:
+            for f in range(f0, f0 + chunk):
                 ctx.upload(f, pin_orig.array[f], pkg.ROLE_CURRENT)
                 ctx.upload(N_FRAMES + f, pin_recon[qp].array[f], pkg.ROLE_REFERENCE)
-            while k < n_pass and passes[k][0] - 1 < f0 + CHUNK:
+            f0 += chunk
+            while k < n_pass and passes[k][0] - 1 < f0:
                 poc, r, refpoc = passes[k]
                 ctx.search(poc - 1, N_FRAMES + refpoc, lambda_for(qp, poc), host_res[k])
                 k += 1
@@ -339,7 +345,7 @@ def run_b200(args, rank, world, local_rank):
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ref_passes_per_s": e2e_fps * n_pass / N_FRAMES},
             "gpu_launches": args.steps * launches_per_flush,
-            "gpu_launches_e2e_per_step": (N_FRAMES // CHUNK) * launches_per_flush + 3 * N_FRAMES,
+            "gpu_launches_e2e_per_step": len(CHUNKS) * launches_per_flush + 3 * N_FRAMES,
             "clocks": clocks,
             "roofline": {"bound": "int32_issue", "achieved": achieved, "peak": peak_tops, "unit": "Tlane-op/s",
                          "frac": achieved / peak_tops, "traffic": traffic,
