@@ -167,3 +167,22 @@ def test_multi_rank_plumbing_gloo():
         p.join(60)
     assert [r[1] for r in res] == [11.0, 11.0]      # max over ranks
     assert [r[2] for r in res] == [128.0, 128.0]    # weak scaling: every rank contributes its own 64 frames
+
+
+@pytest.mark.parametrize("size", ["416x240", "424x236", "1000x600", "1920x1080", "3840x2160"])
+def test_tiled_plane_layout_reader_matches_writer(size, tmp_path_factory):
+    """Host-side check of the tiled layout of the pre-filtered planes (ame_device.h: tile_record): unique indices inside
+    the allocation, and every nine-row window (first row through tile_record, then constant steps) lands on the records
+    the phase kernel's addressing stores for those rows, halo rows included (tests/cpp/tile_layout_check.cpp)."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None or not os.path.isdir("/usr/local/cuda/include"):
+        pytest.skip("needs g++ and the CUDA headers")
+    exe = os.path.join(str(tmp_path_factory.getbasetemp()), "tile_layout_check")
+    if not os.path.exists(exe):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-I/usr/local/cuda/include", "-o", exe,
+                               os.path.join(ROOT, "tests", "cpp", "tile_layout_check.cpp")])
+    w, h = size.split("x")
+    r = subprocess.run([exe, w, h], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("ok ")
