@@ -350,7 +350,7 @@ def run_b200(args, rank, world, local_rank):
             "clocks": clocks,
             "roofline": {"bound": "int32_issue", "achieved": achieved, "peak": peak_tops, "unit": "Tlane-op/s",
                          "frac": achieved / peak_tops, "traffic": traffic,
-                         "traffic_note": "DRAM bytes per launch pair (= per step of 250 passes), extrapolated from the ncu --set full capture "
+                         "traffic_note": "DRAM bytes per launch sequence (= per step of 250 passes), extrapolated from the ncu launch list with DRAM counters "
                                          "recorded in profiles/r01_traffic.json; algorithmic bytes per step = %d" % (ALGO_BYTES_PER_PASS * n_pass),
                          "note": "SURVEY 8(d): compute-bound on INT32 issue; achieved = as-written op model (%.1f G lane-ops/pass) x "
                                  "passes/s per GPU; peak = 148 SM x 4 x 32 lanes x %.0f MHz sampled during the run; algorithmic DRAM "

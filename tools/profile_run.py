@@ -1,4 +1,4 @@
-"""Small fixed workload for ncu: N 1080p frames (default 4 -> 10 reference passes) in one launch pair,
+"""Small fixed workload for ncu: N 1080p frames (default 4 -> 10 reference passes) in one launch sequence,
 repeated --reps times.  Prints device ms per rep.  Not a benchmark."""
 import argparse
 import os
