@@ -1,29 +1,39 @@
 #!/usr/bin/env python
-"""bench.py -- throughput of the affine-ME hot path on synthetic 1080p 10-bit frames.
+"""bench.py -- throughput of the affine-ME hot path on synthetic 10-bit frames.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 1080p|4k|8k|shard4096]
 
-Workload (BASELINE.json configs[1]): 1920x1080, 64 frames with global zoom/rotation/
-translation (tools/synth_frames.py); one STEP = the whole 64-frame sequence = 250 reference
-passes (frame poc runs min(4, poc) passes, main.cpp:584,746) at QP = (22, 27, 32, 37)[step % 4].
-`value` = 1080p frames/s with the reference's multi-reference semantics; ref-passes/s is reported
-beside it.  N > 1 (torchrun, one rank per GPU): every rank runs the same amount of work on its
-own GPU (weak scaling, no inter-GPU traffic), value = all ranks' frames / max-over-ranks time.
+Configurations (BASELINE.json `configs`; the default is the one the metric is quoted on):
+  1080p     configs[1]: 1920x1080, 64 frames with global zoom/rotation/translation (tools/synth_frames.py); one STEP
+            = the whole sequence = 250 reference passes (frame poc runs min(4, poc) passes, main.cpp:584,746) at
+            QP = (22, 27, 32, 37)[step % 4].  N > 1: every rank runs the same sequence (weak scaling).
+  4k        configs[2]: 3840x2160, 64 frames, QP 32 (250 passes per step); weak scaling like 1080p.
+  8k        configs[3]: 7680x4320, 16 frames, QP 32 (58 passes per step).
+  shard4096 configs[4]: ONE batch of 4096 1080p frames (64 repeats of the 64-frame sequence, QP 32) cut into blocks
+            of 8 frames that are dealt round-robin to the ranks (strong scaling, no inter-GPU traffic); one step =
+            the whole batch = 16 000 passes.
+`value` = frames/s of the named size with the reference's multi-reference semantics, whole job over all ranks;
+ref-passes/s is reported beside it.
 
-  value : planes resident in HBM before the timed region, results left in HBM;
-          device time from CUDA events on the context's stream.
-  e2e   : same step through the C ABI with HOST buffers: pinned planes uploaded and every
-          search's costs/CPMVs copied back inside the timed region.
-  roofline : SURVEY.md 8(d): the path is bound by the INT32 issue rate (algorithmic DRAM traffic
-          is ~11 MB per pass); achieved = as-written op model x passes/s, peak = 148 SMs x 4 x 32
-          lanes x the SM clock sampled during the run.
-  cpu_baseline : the CPU oracle (a port of the reference's OpenCL kernels, oracle/ame_oracle.c)
-          on the host cores, rank 0, on a bounded sample.
+  value : raw planes resident in HBM before the timed region, results left in HBM; the timed region runs the plane
+          preparation (block order; edge replication + horizontal filter stage for 16 phases) and the search
+          kernels.  Device time from CUDA events on the context's streams, max over ranks.
+  e2e   : same step through the C ABI with HOST buffers: pinned planes uploaded and every search's costs/CPMVs
+          copied back inside the timed region.
+  parity: passes of the e2e steps are compared with the CPU oracle after the timing (rank 0):
+          parity_checked = CUs compared, mismatches must be 0 (the run fails otherwise).
+  roofline : SURVEY.md 8(d): the path is bound by the INT32 issue rate (algorithmic DRAM traffic is ~13 MB per
+          pass); achieved = op model x passes/s, peak = 148 SMs x 4 x 32 lanes x the SM clock sampled during the run.
+          issue_frac_sequence = executed warp instructions (per-kernel smsp__inst_executed table of
+          profiles/r02_inst_table.json, valid only for the kernel sources it was measured on) x passes/s / peak.
+  cpu_baseline : the CPU oracle (a port of the reference's OpenCL kernels, oracle/ame_oracle.c) on the host
+          cores, rank 0, N = 1 only, on a bounded sample.
 
---impl reference times that CPU port alone (the reference's own OpenCL kernels cannot run on
-the host: there is no CPU OpenCL runtime in the image).
+--impl reference times that CPU port alone (the reference's own OpenCL kernels cannot run on the host: there is no
+CPU OpenCL runtime in the image), on all host cores whatever OMP_NUM_THREADS torchrun sets.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -37,14 +47,47 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-W, H, N_FRAMES = 1920, 1080, 64
 QPS = (22, 27, 32, 37)
-WORKLOAD = "synthetic 1080p 10-bit, 64 frames with global zoom/rotation, QP sweep 22/27/32/37 (one QP per step)"
+CONFIGS = {
+    # name: (W, H, frames per sequence, QPs, sequences per step, workload string)
+    "1080p": (1920, 1080, 64, QPS, 1, "synthetic 1080p 10-bit, 64 frames with global zoom/rotation, QP sweep 22/27/32/37 (one QP per step)"),
+    "4k": (3840, 2160, 64, (32,), 1, "synthetic 4K 3840x2160, 64 frames, QP 32"),
+    "8k": (7680, 4320, 16, (32,), 1, "synthetic 8K 7680x4320, 16 frames, QP 32"),
+    "shard4096": (1920, 1080, 64, (32,), 64, "synthetic 1080p batch of 4096 frames (64 x the 64-frame sequence, QP 32) frame-sharded across the ranks in blocks of 8"),
+}
+SHARD_BLOCK = 8
+# kept as module globals for tools/ and tests/ (the 1080p configuration)
+W, H, N_FRAMES = 1920, 1080, 64
+WORKLOAD = CONFIGS["1080p"][5]
 N_CTUS = 135
-# S = sum over in-frame CUs of w*h; OPS = S * (11*40.2 + 5*45 + 4*71) int32 lane-ops per pass
+
+
+def in_frame_samples(w, h):
+    """S of SURVEY.md 8(d): sum of w*h over the CUs of all 36 groups that lie inside a w x h frame."""
+    import oracle_binding as ob
+    geo = [[ob.cu_geometry(ha, k)[1] for k in range(201 if ha == 0 else 284)] for ha in (0, 1)]
+    s = 0
+    for cy in range(0, h, 128):
+        for cx in range(0, w, 128):
+            for ha in (0, 1):
+                for (x, y, cw, ch) in geo[ha]:
+                    if cx + x + cw <= w and cy + y + ch <= h:
+                        s += cw * ch
+    return s
+
+
+# SURVEY.md 8(d): OPS = S * (11*40.2 + 5*45 + 4*71) int32 lane-ops per pass as the reference writes the work;
+# with the per-sub-block factorisation of the system build the last two terms are 13 + 8 per sample.
 S_1080P = 42585600
-OPS_PER_PASS = S_1080P * (11 * 40.2 + 5 * (13 + 32) + 4 * (13 + 58))
-ALGO_BYTES_PER_PASS = 2 * W * H * 2 + 2 * N_CTUS * (201 + 284) * (8 + 28)
+S_BY_SIZE = {(1920, 1080): S_1080P, (3840, 2160): 172154880, (7680, 4320): 693196800}
+OPS_PER_SAMPLE = 11 * 40.2 + 5 * (13 + 32) + 4 * (13 + 58)
+OPS_PER_SAMPLE_FACTORISED = 11 * 40.2 + 9 * (13 + 8)
+OPS_PER_PASS = S_1080P * OPS_PER_SAMPLE
+
+
+def algo_bytes_per_pass(w, h):
+    nctu = ((w + 127) // 128) * ((h + 127) // 128)
+    return 2 * w * h * 2 + 2 * nctu * (201 + 284) * (8 + 28)
 
 
 # ----------------------------------------------------------------------------- host-side schedule
@@ -97,24 +140,29 @@ def lambda_for(qp, poc):
     return float(np.float32(_FULL_LAMBDAS[q]))
 
 
-def _gen_frame(t):
+def _gen_frame(args):
     import synth_frames as sf
-    return sf.frame(t, W, H)
+    t, w, h = args
+    return sf.frame(t, w, h)
 
 
-def make_sequences():
-    """frames 0..64 (shared by all QPs) and the per-QP reconstructed (noisy) sets."""
+def make_sequences(w=None, h=None, n_frames=None, qps=QPS):
+    """frames 1..n (originals) and, per QP, the reconstructed (noisy) frames 0..n-1."""
     import multiprocessing as mp
     import synth_frames as sf
+    w, h, n_frames = w or W, h or H, n_frames or N_FRAMES
     with mp.get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:
-        frames = pool.map(_gen_frame, range(N_FRAMES + 1))
+        frames = pool.map(_gen_frame, [(t, w, h) for t in range(n_frames + 1)])
     frames = np.stack(frames)
     recon = {}
-    for qp in QPS:
+    for qp in qps:
         a = {22: 1, 27: 2, 32: 3, 37: 5}[qp]
         rng = np.random.Generator(np.random.PCG64(sf.SEED + 1000 * qp))
-        noise = rng.integers(-a, a + 1, size=(N_FRAMES, H, W), dtype=np.int16)
-        recon[qp] = np.clip(frames[:-1].astype(np.int16) + noise, 0, 1023).astype(np.uint16)
+        out = np.empty((n_frames, h, w), np.uint16)
+        for f in range(n_frames):  # (frame by frame: an 8K noise block of all frames would not fit comfortably)
+            noise = rng.integers(-a, a + 1, size=(h, w), dtype=np.int16)
+            out[f] = np.clip(frames[f].astype(np.int16) + noise, 0, 1023).astype(np.uint16)
+        recon[qp] = out
     return frames[1:], recon
 
 
@@ -151,55 +199,113 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------- CPU port (oracle)
-def cpu_port_rate(orig, recon, qp, rows, threads=0):
-    """Times the CPU oracle on the first `rows` CTU rows of one 1080p pass (poc 1, ref 0).
-    Returns (frames/s extrapolated to a full pass, seconds, cores)."""
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_port_rate(cur, ref, qp, rows, frames_per_pass_ratio, threads=0):
+    """Times the CPU oracle on the first `rows` CTU rows of one reference pass (poc 1, ref 0) of the given planes.
+    Returns (frames/s extrapolated to a full pass, passes/s, seconds, cores).  The thread count is always passed
+    explicitly (torchrun exports OMP_NUM_THREADS=1)."""
     import oracle_binding as ob
-    hh = min(H, rows * 128)
-    cur = np.ascontiguousarray(orig[0][:hh])
-    ref = np.ascontiguousarray(recon[0][:hh])
+    h, w = cur.shape
+    hh = min(h, rows * 128)
+    c = np.ascontiguousarray(cur[:hh])
+    r = np.ascontiguousarray(ref[:hh])
     lam = ob.lambda_for(qp, 1)
+    cores = threads if threads > 0 else host_cores()
     t = time.perf_counter()
-    ob.ref_pass(ref, cur, lam, ob.default_opts(threads=threads))
+    ob.ref_pass(r, c, lam, ob.default_opts(threads=cores))
     dt = time.perf_counter() - t
-    frac = (rows * 15) / float(N_CTUS) if hh < H else 1.0
+    ctu_cols, ctu_rows = (w + 127) // 128, (h + 127) // 128
+    frac = (rows * ctu_cols) / float(ctu_cols * ctu_rows) if hh < h else 1.0
     passes_per_s = frac / dt
-    cores = threads if threads > 0 else (os.cpu_count() or 1)
-    return passes_per_s * N_FRAMES / 250.0, passes_per_s, dt, cores
+    return passes_per_s * frames_per_pass_ratio, passes_per_s, dt, cores
 
 
 def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path = the oracle port, all host cores, rank 0 only."""
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
     import synth_frames as sf
-    frames = [sf.frame(t, W, H) for t in (0, 1)]
-    orig = np.stack(frames[1:])
+    w, h, n_frames, qps, n_seq, workload = CONFIGS[args.config]
+    lists = ref_lists(n_frames)
+    n_pass = sum(len(x) for x in lists)
+    frames = [sf.frame(t, w, h) for t in (0, 1)]
     rng = np.random.Generator(np.random.PCG64(sf.SEED + 1000 * 32))
-    recon = np.clip(np.stack(frames[:1]).astype(np.int16) + rng.integers(-3, 4, size=(1, H, W), dtype=np.int16), 0, 1023).astype(np.uint16)
-    rows = 3
+    recon = np.clip(frames[0].astype(np.int16) + rng.integers(-3, 4, size=(h, w), dtype=np.int16), 0, 1023).astype(np.uint16)
+    rows = {"1080p": 3, "4k": 2, "8k": 1, "shard4096": 3}[args.config]
+    ratio = n_frames / float(n_pass)
     for _ in range(args.warmup):
-        cpu_port_rate(orig, recon, 32, rows)
+        cpu_port_rate(frames[1], recon, 32, rows, ratio)
     t0 = time.perf_counter()
     fps = []
+    cores = host_cores()
     for _ in range(args.steps):
-        f, p, dt, cores = cpu_port_rate(orig, recon, 32, rows)
+        f, p, dt, cores = cpu_port_rate(frames[1], recon, 32, rows, ratio)
         fps.append(f)
     total = time.perf_counter() - t0
     v = float(np.mean(fps))
-    sample = "CTU rows 0-%d of one 1080p reference pass (poc 1, ref 0, QP 32) per step, extrapolated by CTU count" % (rows - 1)
-    line = {"impl": "reference", "metric": "1080p frames/sec affine ME", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+    sample = "CTU rows 0-%d of one %dx%d reference pass (poc 1, ref 0, QP 32) per step, extrapolated by CTU count" % (rows - 1, w, h)
+    line = {"impl": "reference", "metric": "%s frames/sec affine ME" % size_name(w, h), "value": v, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / max(args.steps, 1),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": N_FRAMES, "ref_passes_per_step": 250,
+            "higher_is_better": True, "scaling": "strong" if args.config == "shard4096" else "weak", "vs_baseline": None,
+            "dtype": "int32+f64", "data": "synthetic",
+            "config": {"workload": workload, "frames_per_step": n_frames * n_seq, "ref_passes_per_step": n_pass * n_seq,
                        "note": "CPU arm: each step times a bounded sample of this workload (see cpu_baseline.sample)"},
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "ref_passes_per_s": v * 250.0 / N_FRAMES}
+            "ref_passes_per_s": v / ratio}
     print(json.dumps(line), flush=True)
 
 
+def size_name(w, h):
+    return {(1920, 1080): "1080p", (3840, 2160): "4K", (7680, 4320): "8K"}.get((w, h), "%dx%d" % (w, h))
+
+
+# ----------------------------------------------------------------------------- evidence that goes stale with the kernels
+def kernel_source_sha():
+    hsh = hashlib.sha256()
+    d = os.path.join(ROOT, "vvc-affine-gpu_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".h")):
+            hsh.update(open(os.path.join(d, name), "rb").read())
+    return hsh.hexdigest()[:16]
+
+
+def inst_table(config):
+    """Executed warp instructions per reference pass from the committed ncu table, or (None, why)."""
+    path = os.path.join(ROOT, "profiles", "r02_inst_table.json")
+    try:
+        t = json.load(open(path))
+    except Exception:
+        return None, "profiles/r02_inst_table.json missing"
+    if t.get("kernel_source_sha") != kernel_source_sha():
+        return None, "stale: measured on kernel sources %s, this build is %s" % (t.get("kernel_source_sha"), kernel_source_sha())
+    e = t.get("configs", {}).get(config)
+    if not e:
+        return None, "no entry for config %s" % config
+    return e, None
+
+
 # ----------------------------------------------------------------------------- the B200 arm
+def step_plan(n_frames, n_seq, sharded, rank, world):
+    """What one rank runs in one step: a list of launch sequences, each a list of frame ranges [f0, f1) of the
+    n_frames-frame cycle.  Unsharded: the whole sequence on every rank.  Sharded (configs[4]): the batch of
+    n_seq * n_frames frames in blocks of SHARD_BLOCK frames, block b on rank b % world (no exchange step: a block
+    needs only planes of the input files); a rank's blocks are grouped into sequences of 8 blocks."""
+    if not sharded:
+        return [[(0, n_frames)]]
+    blocks_per_seq = n_frames // SHARD_BLOCK
+    my_blocks = [b for b in range(n_seq * blocks_per_seq) if b % world == rank]
+    group = 8
+    return [[((b % blocks_per_seq) * SHARD_BLOCK, (b % blocks_per_seq) * SHARD_BLOCK + SHARD_BLOCK) for b in my_blocks[i:i + group]]
+            for i in range(0, len(my_blocks), group)]
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     from conftest import load_pkg
@@ -222,44 +328,56 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    orig, recon = make_sequences()
-    lists = ref_lists(N_FRAMES)
-    passes = [(poc, r, lists[poc - 1][r]) for poc in range(1, N_FRAMES + 1) for r in range(len(lists[poc - 1]))]
-    assert len(passes) == 250
+    w, h, n_frames, qps, n_seq, workload = CONFIGS[args.config]
+    sharded = args.config == "shard4096"
+    orig, recon = make_sequences(w, h, n_frames, qps)
+    lists = ref_lists(n_frames)
+    passes = [(poc, r, lists[poc - 1][r]) for poc in range(1, n_frames + 1) for r in range(len(lists[poc - 1]))]
     n_pass = len(passes)
+    first_pass_of = {}
+    for k, (poc, r, rp) in enumerate(passes):
+        first_pass_of.setdefault(poc - 1, k)
+    first_pass_of[n_frames] = n_pass
 
-    # slots: 0..63 = original frames (poc-1), 64..127 = reconstructed frames 0..63
-    ctx = pkg.AffineME(W, H, device=local_rank, num_slots=2 * N_FRAMES, max_in_flight=n_pass)
+    sequences = step_plan(n_frames, n_seq, sharded, rank, world)
+    total_frames_per_step = n_seq * n_frames if sharded else world * n_frames
+    my_frames_per_step = sum(f1 - f0 for s in sequences for (f0, f1) in s)
+    my_passes_per_step = sum(first_pass_of[f1] - first_pass_of[f0] for s in sequences for (f0, f1) in s)
+    max_seq_passes = max(sum(first_pass_of[f1] - first_pass_of[f0] for (f0, f1) in s) for s in sequences)
+
+    # slots: 0..n-1 = original frames (poc-1), n..2n-1 = reconstructed frames 0..n-1
+    ctx = pkg.AffineME(w, h, device=local_rank, num_slots=2 * n_frames, max_in_flight=max_seq_passes)
     pin_orig = pkg.PinnedArray(orig.shape, np.uint16)
     pin_orig.array[...] = orig
     pin_recon = {}
-    for qp in QPS:
+    for qp in qps:
         pin_recon[qp] = pkg.PinnedArray(recon[qp].shape, np.uint16)
         pin_recon[qp].array[...] = recon[qp]
-    host_res = [pkg.HostResult(ctx) for _ in range(n_pass)]
+    host_res = [pkg.HostResult(ctx) for _ in range(max_seq_passes)]
 
     def upload_all(qp):
-        for f in range(N_FRAMES):
+        for f in range(n_frames):
             ctx.upload(f, pin_orig.array[f], pkg.ROLE_CURRENT)
-            ctx.upload(N_FRAMES + f, pin_recon[qp].array[f], pkg.ROLE_REFERENCE)
+            ctx.upload(n_frames + f, pin_recon[qp].array[f], pkg.ROLE_REFERENCE)
 
-    def queue_all(qp, to_host):
-        for k, (poc, r, refpoc) in enumerate(passes):
-            lam = lambda_for(qp, poc)
-            if to_host:
-                ctx.search(poc - 1, N_FRAMES + refpoc, lam, host_res[k])
-            else:
-                ctx.search_device(poc - 1, N_FRAMES + refpoc, lam, k)
+    def seq_passes(seq):
+        return [k for (f0, f1) in seq for k in range(first_pass_of[f0], first_pass_of[f1])]
 
-    # ---- device-resident timing ----
+    # ---- device-resident timing: preparation of every plane + all launch sequences of the step ----
     def step_resident(step):
-        qp = QPS[step % 4]
-        upload_all(qp)          # untimed: inputs resident before the timed region
+        qp = qps[step % len(qps)]
+        upload_all(qp)          # untimed: raw planes resident before the timed region
         ctx.sync()
         barrier()
-        queue_all(qp, False)    # host-side bookkeeping only; nothing is launched before flush()
         ctx.timer_start()
-        ctx.flush()
+        for f in range(n_frames):
+            ctx.prepare(f, pkg.ROLE_CURRENT)
+            ctx.prepare(n_frames + f, pkg.ROLE_REFERENCE)
+        for seq in sequences:
+            for i, k in enumerate(seq_passes(seq)):
+                poc, r, refpoc = passes[k]
+                ctx.search_device(poc - 1, n_frames + refpoc, lambda_for(qp, poc), i)
+            ctx.sync() if len(sequences) > 1 else ctx.flush()   # (result blocks are reused by the next sequence)
         ms = ctx.timer_stop()
         ctx.sync()
         barrier()
@@ -267,30 +385,67 @@ def run_b200(args, rank, world, local_rank):
 
     # frames per launch sequence in the end-to-end path: uploads of chunk k+1 and result copies of chunk k-1 overlap
     # the kernels of chunk k; the first upload and the last copy overlap nothing, so the first and last chunks are short
-    CHUNK = 8
-    CHUNKS = [int(x) for x in os.environ.get("AME_BENCH_CHUNKS", "").split(",") if x] or [2, 6] + [CHUNK] * ((N_FRAMES - 16) // CHUNK) + [6, 2]
-    assert sum(CHUNKS) == N_FRAMES
+    if sharded:
+        chunks = None
+    else:
+        big = {"1080p": 8, "4k": 4, "8k": 2}[args.config]
+        chunks = [int(x) for x in os.environ.get("AME_BENCH_CHUNKS", "").split(",") if x]
+        if not chunks:
+            head = [c for c in (max(1, big // 4), max(1, (3 * big) // 4)) if c]
+            rest = n_frames - 2 * sum(head)
+            chunks = head + [big] * (rest // big) + ([rest % big] if rest % big else []) + head[::-1]
+        assert sum(chunks) == n_frames, chunks
 
-    def step_e2e(step):
-        qp = QPS[step % 4]
+    checks = []   # (qp, pass index, costs, cpmvs) copied out of the e2e steps for the parity check
+
+    def keep_for_check(step, qp, k, res):
+        checks.append((qp, k, [c.copy() for c in res.cost], [m.copy() for m in res.cpmvs]))
+
+    # the passes compared with the oracle: a different one after every e2e step (short-term, long-term far / near)
+    check_poc_ref = [(1, 0), (12, 2), (37, 1), (n_frames, 3), (5, 3), (24, 2)] if n_frames >= 64 else [(1, 0), (12, 2), (16, 3), (5, 3)]
+
+    def step_e2e(step, check):
+        qp = qps[step % len(qps)]
+        want = None
+        if check:
+            poc, r = check_poc_ref[step % len(check_poc_ref)]
+            want = next(k for k, p in enumerate(passes) if p[0] == poc and p[1] == r)
         barrier()
         t0 = time.perf_counter()
         ctx.timer_start()
-        k = 0
-        f0 = 0
-        for chunk in CHUNKS:
-            for f in range(f0, f0 + chunk):
-                ctx.upload(f, pin_orig.array[f], pkg.ROLE_CURRENT)
-                ctx.upload(N_FRAMES + f, pin_recon[qp].array[f], pkg.ROLE_REFERENCE)
-            f0 += chunk
-            while k < n_pass and passes[k][0] - 1 < f0:
-                poc, r, refpoc = passes[k]
-                ctx.search(poc - 1, N_FRAMES + refpoc, lambda_for(qp, poc), host_res[k])
-                k += 1
-            ctx.flush()
+        if sharded:
+            # every sequence: upload the planes its blocks need, search, read back; sequences pipeline through the streams
+            for seq in sequences:
+                need_cur = sorted({f for (f0, f1) in seq for f in range(f0, f1)})
+                need_ref = sorted({passes[k][2] for k in seq_passes(seq)})
+                for f in need_cur:
+                    ctx.upload(f, pin_orig.array[f], pkg.ROLE_CURRENT)
+                for f in need_ref:
+                    ctx.upload(n_frames + f, pin_recon[qp].array[f], pkg.ROLE_REFERENCE)
+                for i, k in enumerate(seq_passes(seq)):
+                    poc, r, refpoc = passes[k]
+                    ctx.search(poc - 1, n_frames + refpoc, lambda_for(qp, poc), host_res[i])
+                ctx.sync()   # host result buffers are reused by the next sequence
+                if want is not None and want in seq_passes(seq) and not any(c[0] == qp and c[1] == want for c in checks):
+                    keep_for_check(step, qp, want, host_res[seq_passes(seq).index(want)])
+        else:
+            k = 0
+            f0 = 0
+            for chunk in chunks:
+                for f in range(f0, f0 + chunk):
+                    ctx.upload(f, pin_orig.array[f], pkg.ROLE_CURRENT)
+                    ctx.upload(n_frames + f, pin_recon[qp].array[f], pkg.ROLE_REFERENCE)
+                f0 += chunk
+                while k < n_pass and passes[k][0] - 1 < f0:
+                    poc, r, refpoc = passes[k]
+                    ctx.search(poc - 1, n_frames + refpoc, lambda_for(qp, poc), host_res[k])
+                    k += 1
+                ctx.flush()
         ms = ctx.timer_stop()
         ctx.sync()
         wall = (time.perf_counter() - t0) * 1000.0
+        if want is not None and not sharded:
+            keep_for_check(step, qp, want, host_res[want])
         barrier()
         return max(ms, wall)
 
@@ -304,21 +459,40 @@ def run_b200(args, rank, world, local_rank):
     sampler.join()
     clocks = sampler.summary()
     total_ms = max_over_ranks(float(np.sum(times)))
-    frames_per_s = world * N_FRAMES * args.steps / (total_ms / 1000.0)
-    passes_per_s = frames_per_s * n_pass / N_FRAMES
+    frames_per_s = total_frames_per_step * args.steps / (total_ms / 1000.0)
+    passes_per_s = frames_per_s * n_pass / n_frames
 
     for s in range(min(args.warmup, 1)):
-        step_e2e(s)
-    e2e_times = [step_e2e(s) for s in range(args.steps)]
+        step_e2e(s, False)
+    e2e_times = [step_e2e(s, rank == 0) for s in range(args.steps)]
     e2e_ms = max_over_ranks(float(np.sum(e2e_times)))
-    e2e_fps = world * N_FRAMES * args.steps / (e2e_ms / 1000.0)
-    h2d = 2 * N_FRAMES * W * H * 2
-    d2h = n_pass * sum(ctx.result_len(p) * (8 + 28) for p in range(4))
+    e2e_fps = total_frames_per_step * args.steps / (e2e_ms / 1000.0)
+    res_bytes = sum(ctx.result_len(p) * (8 + 28) for p in range(4))
+    if sharded:
+        h2d = sum((len({f for (f0, f1) in s for f in range(f0, f1)}) + len({passes[k][2] for k in seq_passes(s)})) * w * h * 2 for s in sequences)
+    else:
+        h2d = 2 * n_frames * w * h * 2
+    d2h = my_passes_per_step * res_bytes
 
-    # spot check of the last e2e step against... nothing on the CPU here (tests do that); sanity only
-    assert int(host_res[0].cost[0][0]) > 0
-
+    rc = 0
     if rank == 0:
+        # ---- parity of what was timed: kept passes of the e2e steps against the CPU oracle ----
+        import oracle_binding as ob
+        n_cus, bad = 0, 0
+        checked = []
+        for (qp, k, costs, cpmvs) in checks:
+            poc, r, refpoc = passes[k]
+            oc, om = ob.ref_pass(recon[qp][refpoc], orig[poc - 1], ob.lambda_for(qp, poc), ob.default_opts(threads=host_cores()))
+            for p in range(4):
+                m = costs[p] != oc[p]
+                for f in ("LTx", "LTy", "RTx", "RTy", "LBx", "LBy"):
+                    m |= cpmvs[p][f] != om[p][f]
+                bad += int(m.sum())
+                n_cus += len(m)
+            checked.append({"qp": qp, "poc": poc, "ref_idx": r, "ref_poc": refpoc})
+        if bad or not checks:
+            rc = 1
+
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -326,61 +500,69 @@ def run_b200(args, rank, world, local_rank):
             pass
         sm_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
         peak_tops = 148 * 4 * 32 * sm_mhz * 1e6 / 1e12
+        peak_winst = 148 * 4 * sm_mhz * 1e6
         per_gpu_passes = passes_per_s / world
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["dram_bytes_per_ref_pass"] * n_pass
-        except Exception:
-            pass
-        achieved = OPS_PER_PASS * per_gpu_passes / 1e12
+        S = S_BY_SIZE.get((w, h)) or in_frame_samples(w, h)
+        ops_pass = S * OPS_PER_SAMPLE
+        achieved = ops_pass * per_gpu_passes / 1e12
+        achieved_fact = S * OPS_PER_SAMPLE_FACTORISED * per_gpu_passes / 1e12
+        tab, why = inst_table(args.config if args.config != "shard4096" else "1080p")
+        algo_bytes = algo_bytes_per_pass(w, h)
+        issue_frac = traffic = None
+        if tab:
+            issue_frac = tab["warp_inst_per_pass"] * per_gpu_passes / peak_winst
+            if tab.get("dram_bytes_per_pass"):
+                traffic = tab["dram_bytes_per_pass"] * my_passes_per_step
         # the CPU baseline is timed at N = 1 only (the other ranks would spin on the barrier and take its cores)
-        cb = cpu_port_rate(orig, recon[32], 32, N_CTUS // 15) if world == 1 else None
+        cb = None
+        if world == 1:
+            rows = {"1080p": 9, "4k": 6, "8k": 3, "shard4096": 9}[args.config]
+            cb = cpu_port_rate(orig[0], recon[32][0], 32, rows, n_frames / float(n_pass))
         line = {
-            "metric": "1080p frames/sec affine ME", "value": frames_per_s, "unit": "frames/s", "n_gpus": world,
+            "metric": "%s frames/sec affine ME" % size_name(w, h), "value": frames_per_s, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "frames_per_step": N_FRAMES, "ref_passes_per_step": n_pass, "per_gpu": "same sequence on every rank",
-                       "l2": "inputs (1.35 GB of planes per step) larger than L2; no flush"},
+            "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+            "config": {"workload": workload, "name": args.config,
+                       "frames_per_step": total_frames_per_step, "ref_passes_per_step": total_frames_per_step * n_pass // n_frames,
+                       "per_gpu": ("blocks of %d frames, block b on rank b %% %d: %d frames per rank and step" % (SHARD_BLOCK, world, my_frames_per_step))
+                       if sharded else "same sequence on every rank",
+                       "timed_region": "plane preparation (block order, edge replication, horizontal filter stage) + search kernels; raw planes resident",
+                       "l2": "inputs (%.2f GB of raw + prepared planes per step) larger than L2; no flush" % (
+                           n_frames * (2 * w * h * 2 + 32.0 * (w + 320) * (h + 320) * 2) / 1e9)},
             "ref_passes_per_s": passes_per_s,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ref_passes_per_s": e2e_fps * n_pass / N_FRAMES},
-            "gpu_launches": args.steps * launches_per_flush,
-            "gpu_launches_e2e_per_step": len(CHUNKS) * launches_per_flush + 3 * N_FRAMES,
+                    "ref_passes_per_s": e2e_fps * n_pass / n_frames},
+            "parity_checked": n_cus, "mismatches": bad, "parity_passes": checked,
+            "gpu_launches": args.steps * (launches_per_flush * len(sequences) + 3 * n_frames),
+            "gpu_launches_e2e_per_step": (len(sequences) if sharded else len(chunks)) * launches_per_flush + 3 * n_frames,
             "clocks": clocks,
             "roofline": {"bound": "int32_issue", "achieved": achieved, "peak": peak_tops, "unit": "Tlane-op/s",
-                         "frac": achieved / peak_tops, "traffic": traffic,
-                         "traffic_note": "DRAM bytes per launch sequence (= per step of 250 passes), extrapolated from the ncu launch list with DRAM counters "
-                                         "recorded in profiles/r01_traffic.json; algorithmic bytes per step = %d" % (ALGO_BYTES_PER_PASS * n_pass),
-                         "note": "SURVEY 8(d): compute-bound on INT32 issue; achieved = as-written op model (%.1f G lane-ops/pass) x "
-                                 "passes/s per GPU; peak = 148 SM x 4 x 32 lanes x %.0f MHz sampled during the run; algorithmic DRAM "
-                                 "bytes/pass = %d (%.1f GB/s, vs %.0f GB/s measured HBM peak)" % (
-                                     OPS_PER_PASS / 1e9, sm_mhz, ALGO_BYTES_PER_PASS, ALGO_BYTES_PER_PASS * per_gpu_passes / 1e9,
+                         "frac": achieved / peak_tops, "frac_factorised_model": achieved_fact / peak_tops,
+                         "issue_frac_sequence": issue_frac, "inst_table": tab if tab else why,
+                         "traffic": traffic,
+                         "traffic_note": "DRAM bytes per step on this rank = ncu dram__bytes_read+write over one launch sequence of this workload "
+                                         "(profiles/r02_inst_table.json) / its passes x passes per step; algorithmic bytes per step = %d" % (algo_bytes * my_passes_per_step),
+                         "note": "SURVEY 8(d): compute-bound on INT32 issue.  achieved / frac = as-written op model (%.1f G lane-ops/pass) x passes/s per GPU "
+                                 "over peak = 148 SM x 4 x 32 lanes x %.0f MHz sampled during the run; it can exceed 1 because the exact shortcuts "
+                                 "(early exit on a revisited state, shared first 2-CP evaluation, 3-CP start reuse) skip work the model counts: "
+                                 "it is NOT a utilisation.  frac_factorised_model = the same with the factorised system build (%.1f G).  "
+                                 "issue_frac_sequence = executed warp instructions of the whole launch sequence (ncu smsp__inst_executed) x passes/s "
+                                 "over 148 x 4 x f_SM issue slots: the hardware-side utilisation.  Algorithmic DRAM bytes/pass = %d (%.1f GB/s of %.0f GB/s measured)" % (
+                                     ops_pass / 1e9, sm_mhz, S * OPS_PER_SAMPLE_FACTORISED / 1e9, algo_bytes, algo_bytes * per_gpu_passes / 1e9,
                                      peaks.get("hbm_gbs", 6650.0)),
-                         "frac_note": "the op model counts the work as the reference writes it; the exact shortcuts (early exit on a "
-                                      "revisited state, shared first 2-CP evaluation, 3-CP start reuse) skip part of it, so frac can "
-                                      "exceed 1 -- ncu_issue_active_pct is the hardware-side figure of the dominant kernel",
-                         "ncu_issue_active_pct": ncu_issue_active(),
-                         "kernel_ms_per_step": kernel_ms},
+                         "kernel_ms_last_sequence": kernel_ms},
             "cpu_baseline": None if cb is None else {
                 "value": cb[0], "unit": "frames/s", "cores": cb[3], "kind": "port",
-                "sample": "one full 1080p reference pass (poc 1, ref 0, QP 32), %.1f s" % cb[2], "ref_passes_per_s": cb[1]},
+                "sample": "CTU rows 0-%d of one %dx%d reference pass (poc 1, ref 0, QP 32), %.1f s, extrapolated by CTU count" % (
+                    min(rows, (h + 127) // 128) - 1, w, h, cb[2]), "ref_passes_per_s": cb[1]},
         }
         print(json.dumps(line), flush=True)
+        if rc:
+            print("bench.py: PARITY FAILURE: %d of %d CUs differ from the oracle (or nothing was checked)" % (bad, n_cus), file=sys.stderr, flush=True)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
-
-
-def ncu_issue_active():
-    """smsp__issue_active of ame_iter_small (60 % of the step) from the committed ncu --set full capture, or None."""
-    try:
-        for ln in open(os.path.join(ROOT, "profiles", "r01_final_ncu_ame_iter_small.txt")):
-            if ln.startswith("smsp__issue_active.avg.pct_of_peak_sustained_active"):
-                return float(ln.split()[-1])
-    except OSError:
-        pass
-    return None
+    return rc
 
 
 def main():
@@ -389,15 +571,16 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="1080p", choices=sorted(CONFIGS))
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
-    else:
-        run_b200(args, rank, world, local_rank)
+        return 0
+    return run_b200(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main())

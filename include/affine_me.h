@@ -35,6 +35,8 @@
  * contexts share nothing.  All functions return 0 on success or a negative
  * AME_E_* code; ame_last_error() returns the message of the calling thread's
  * last failure.  There is no CPU fallback: without a CUDA device ame_create fails.
+ * A CUDA error after work has been issued (ame_flush / ame_sync) makes the context unusable: the searches in flight
+ * are dropped, every later call returns AME_E_CUDA with the first error, ame_destroy frees it.
  */
 #ifndef AFFINE_ME_H
 #define AFFINE_ME_H
@@ -120,6 +122,12 @@ int ame_upload_plane(ame_ctx *ctx, int slot, const uint16_t *plane);
 enum { AME_ROLE_CURRENT = 1, AME_ROLE_REFERENCE = 2 };
 int ame_upload_plane_ex(ame_ctx *ctx, int slot, const uint16_t *plane, int roles);
 
+/* Runs the preparation of ame_upload_plane_ex again on the plane that is already resident in `slot` (no host-to-device
+ * copy): the block-ordered copy (AME_ROLE_CURRENT) and / or edge replication + the horizontal interpolation stage for
+ * all 16 phases (AME_ROLE_REFERENCE; that stage is half of aux_functions.cl:1096-1239, run once per plane here instead
+ * of once per sub-block and iteration).  bench.py uses it to time that work with the inputs already in HBM. */
+int ame_prepare_plane(ame_ctx *ctx, int slot, int roles);
+
 /* Queues one search of the plane in cur_slot against the plane in ref_slot.
  * `out` arrays are HOST memory and are valid after the next ame_sync.
  * extra_iters == --ExtraGradientIter. */
@@ -130,6 +138,13 @@ int ame_search(ame_ctx *ctx, int cur_slot, int ref_slot, float lambda, int extra
 int ame_search_device(ame_ctx *ctx, int cur_slot, int ref_slot, float lambda, int extra_iters, int result_index);
 int ame_device_result(ame_ctx *ctx, int result_index, ame_result *out); /* result_index < max_in_flight */
 
+/* Result arrays in ONE block of host memory, laid out like the library's device-side result block:
+ * ame_result_bind points the eight arrays of `out` into `block` (ame_result_block_bytes bytes, e.g. from
+ * ame_alloc_host).  A search whose destination was bound this way comes back with one device-to-host copy
+ * instead of eight (the reference reads its result buffers one by one, main_aux_functions.h:335-383). */
+uint64_t ame_result_block_bytes(const ame_ctx *ctx);
+int ame_result_bind(const ame_ctx *ctx, void *block, ame_result *out);
+
 /* Launches everything queued so far without waiting. */
 int ame_flush(ame_ctx *ctx);
 /* ame_flush + wait for all queued uploads, searches and result copies. */
@@ -139,9 +154,18 @@ int ame_sync(ame_ctx *ctx);
  * launched by the most recent ame_flush/ame_sync, and their launch count. */
 int ame_last_kernel_ms(ame_ctx *ctx, float *ms, int *launches);
 
+/* Device time, in nanoseconds, of the searches run since the last reset, per prediction type in the reference's
+ * order (kernelExecutionTime[FULL_2CP..HALF_3CP], main.cpp:862-866, 949-953, printed by reportTimingResults,
+ * main_aux_functions.h:1416-1446).  The four types run fused here: the 2-CP searches of a launch sequence (aligned
+ * and half-aligned CUs together) are timed as one interval on the device and so are the 3-CP searches; each
+ * interval is split between FULL and HALF by the number of 4x4 sub-block evaluations either side accounted for.
+ * Needs ame_sync first. */
+int ame_exec_ns(ame_ctx *ctx, double ns[AME_N_PREDS], int reset);
+
 /* Device-side stopwatch on the context's stream (CUDA events): ame_timer_start records the start event
  * behind everything issued so far, ame_timer_stop records the stop event, waits for it and returns the
- * elapsed milliseconds.  Used by bench.py; the events see uploads, kernels and result copies alike. */
+ * elapsed milliseconds.  Used by bench.py; the events see uploads, kernels and result copies alike (the start
+ * mark waits for whatever was issued before it on the upload and result streams, too). */
 int ame_timer_start(ame_ctx *ctx);
 int ame_timer_stop(ame_ctx *ctx, float *ms);
 

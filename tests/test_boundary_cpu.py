@@ -87,6 +87,29 @@ def test_cli_flag_surface():
     assert r.returncode != 0
 
 
+@pytest.mark.skipif(not os.path.exists(CLI), reason="CLI not built")
+@pytest.mark.parametrize("qp", [22, 27, 32, 37])
+def test_product_schedule_matches_oracle(qp):
+    """The PRODUCT's reference-list and lambda schedule (host/schedule.cpp, compiled into affine_b200) for POC 1..64,
+    long-term references included, against the oracle's restatement of main.cpp:591-707 and
+    main_aux_functions.h:1473-1497.  The CLI prints its plan (testReferences, main_aux_functions.h:1499-1545; that
+    loop stops one frame short, hence -f 65) before it touches the GPU, so this runs without one: the exit code is
+    not looked at (without a device the CLI stops at the pinned allocation, with one at the missing input files)."""
+    import re
+    r = subprocess.run([CLI, "-f", "65", "-s", "416x240", "-q", str(qp), "-o", "/nonexistent/o.csv", "-r", "/nonexistent/r.csv"],
+                       capture_output=True, text=True)
+    rows = re.findall(r"^POC +(\d+) +QP (\d+) motionLambda ([0-9.]+) : \[L0([ 0-9-]*)\]$", r.stdout, re.M)
+    assert [int(x[0]) for x in rows] == list(range(1, 65)), r.stdout[-1500:]
+    lists = ob.ref_lists(64)
+    for poc_s, q_s, lam_s, refs_s in rows:
+        poc = int(poc_s)
+        assert [int(v) for v in refs_s.split()] == lists[poc - 1], poc
+        assert int(q_s) == ob.delta_qp(qp, poc), poc
+        assert lam_s == "%f" % ob.lambda_for(qp, poc), poc
+    # the long-term branch was really exercised: POC 64 keeps POC%8==0 frames far behind it
+    assert lists[63] != [63, 62, 61, 60] and any(v % 8 == 0 and v < 56 for v in lists[63])
+
+
 def test_bench_schedule_helpers_match_oracle():
     sys.path.insert(0, ROOT)
     import bench
@@ -95,6 +118,25 @@ def test_bench_schedule_helpers_match_oracle():
         for poc in range(1, 40):
             assert bench.lambda_for(qp, poc) == ob.lambda_for(qp, poc)
     assert bench.OPS_PER_PASS == pytest.approx(40.5e9, rel=0.01)
+
+
+def test_bench_shard_plan_covers_the_batch_once():
+    """configs[4]: the 4096-frame batch is dealt to the ranks in blocks of 8 frames; every block exactly once."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for world in (1, 2, 4, 8):
+        seen = []
+        for rank in range(world):
+            plan = bench.step_plan(64, 64, True, rank, world)
+            frames = sum(f1 - f0 for seq in plan for (f0, f1) in seq)
+            assert frames == 4096 // world
+            assert all(len(seq) <= 8 and all(f1 - f0 == bench.SHARD_BLOCK and f0 % 8 == 0 for f0, f1 in seq) for seq in plan)
+            seen += [(i, j) for i, seq in enumerate(plan) for j in range(len(seq))]
+        assert len(seen) == 512
+    assert bench.step_plan(64, 1, False, 3, 8) == [[(0, 64)]]
+    # S of SURVEY 8(d), recomputed from the geometry tables
+    assert bench.in_frame_samples(1920, 1080) == bench.S_1080P
+    assert bench.in_frame_samples(3840, 2160) == bench.S_BY_SIZE[(3840, 2160)]
 
 
 def test_log_reader_roundtrip(tmp_path):

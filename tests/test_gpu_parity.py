@@ -232,11 +232,111 @@ def test_1080p_properties(pkg):
         assert (a == b).all()
 
 
+def test_full_1080p_frames_match_oracle_at_every_qp(pkg):
+    """BASELINE.json configs[1]: whole 1080p frames (135 CTUs, partial bottom row) of the bench sequence, one pass per QP
+    of the sweep, short-term and long-term references (POC 12 searches POC 8, POC 24 searches POC 8: the large-motion
+    case where searches do not converge), every logged CU against the oracle."""
+    W, H = 1920, 1080
+    lists = ob.ref_lists(24)
+    cases = [(22, 1, 0), (27, 5, 3), (32, 12, 2), (37, 24, 2)]  # (QP, poc, reference index)
+    assert lists[11][2] == 8 and lists[23][2] == 8
+    ctx = pkg.AffineME(W, H, num_slots=2, max_in_flight=1)
+    try:
+        for qp, poc, r in cases:
+            refpoc = lists[poc - 1][r]
+            cur = sf.frame(poc, W, H)
+            a = {22: 1, 27: 2, 32: 3, 37: 5}[qp]
+            rng = np.random.Generator(np.random.PCG64(sf.SEED + 1000 * qp + refpoc))
+            ref = np.clip(sf.frame(refpoc, W, H).astype(np.int64) + rng.integers(-a, a + 1, size=(H, W)), 0, 1023).astype(np.uint16)
+            lam = ob.lambda_for(qp, poc)
+            costs, cp = ctx.ref_pass(ref, cur, lam)
+            oc, om = ob.ref_pass(ref, cur, lam)
+            assert _diff(costs, cp, oc, om) == 0, (qp, poc, r)
+    finally:
+        ctx.close()
+
+
+def _sequence_passes(n):
+    lists = ob.ref_lists(n)
+    return [(poc, r, lists[poc - 1][r]) for poc in range(1, n + 1) for r in range(len(lists[poc - 1]))]
+
+
+def test_twelve_frame_sequence_matches_oracle(pkg):
+    """A 12-frame 416x240 sequence with the reference's multi-reference schedule (42 passes; from POC 9 on the lists
+    hold the long-term POC 8 / POC 0 planes) as ONE launch sequence, every pass against the oracle."""
+    W, H, n, qp = 416, 240, 12, 27
+    orig, recon = sf.sequences(n, W, H, qp, seed=sf.SEED + 91)
+    passes = _sequence_passes(n)
+    assert len(passes) == 42 and any(rp == 0 and poc >= 9 for poc, _, rp in passes)
+    ctx = pkg.AffineME(W, H, num_slots=2 * n, max_in_flight=len(passes))
+    try:
+        for f in range(n):
+            ctx.upload(f, orig[f], pkg.ROLE_CURRENT)
+            ctx.upload(n + f, recon[f], pkg.ROLE_REFERENCE)
+        res = [pkg.HostResult(ctx, separate=(k % 2 == 1)) for k in range(len(passes))]  # both destination layouts
+        for k, (poc, r, rp) in enumerate(passes):
+            ctx.search(poc - 1, n + rp, ob.lambda_for(qp, poc), res[k])
+        ctx.sync()
+        for k, (poc, r, rp) in enumerate(passes):
+            oc, om = ob.ref_pass(recon[rp], orig[poc - 1], ob.lambda_for(qp, poc))
+            assert _diff(res[k].cost, res[k].cpmvs, oc, om) == 0, (poc, r)
+        ns = ctx.exec_ns(reset=True)
+        assert len(ns) == 4 and all(v > 0 for v in ns)
+        assert ctx.exec_ns() == [0.0, 0.0, 0.0, 0.0]
+        for r_ in res:
+            r_.free()
+    finally:
+        ctx.close()
+
+
+def test_overlapped_pipeline_matches_oracle(pkg):
+    """The end-to-end pipeline of bench.py / the CLI: uploads and ame_flush in chunks WITHOUT ame_sync in between
+    (descriptor slots at an offset, uploads running beside kernels in flight), with so few plane slots that a slot
+    still in use by an in-flight search is overwritten (the upload must wait for those kernels); every result against
+    the oracle."""
+    W, H, n, qp = 416, 240, 10, 32
+    orig, recon = sf.sequences(n, W, H, qp, seed=sf.SEED + 93)
+    passes = _sequence_passes(n)
+    ncur, nref = 3, 6   # current frames rotate through 3 slots, references through 6 (a frame needs up to 4 + the next one)
+    ctx = pkg.AffineME(W, H, num_slots=ncur + nref, max_in_flight=len(passes))
+    try:
+        res = [pkg.HostResult(ctx) for _ in passes]
+        ref_slot = {}
+        k = 0
+        for f in range(n):                      # chunk = one frame
+            ctx.upload(f % ncur, orig[f], pkg.ROLE_CURRENT)
+            for (poc, r, rp) in passes:
+                if poc - 1 == f and rp not in ref_slot:
+                    # evict the slot of the oldest reference that this and later frames no longer need
+                    if len(ref_slot) == nref:
+                        needed = {p[2] for p in passes if p[0] - 1 >= f}
+                        victim = min(x for x in ref_slot if x not in needed)
+                        ref_slot[rp] = ref_slot.pop(victim)
+                    else:
+                        ref_slot[rp] = ncur + len(ref_slot)
+                    ctx.upload(ref_slot[rp], recon[rp], pkg.ROLE_REFERENCE)
+            while k < len(passes) and passes[k][0] - 1 == f:
+                poc, r, rp = passes[k]
+                ctx.search(f % ncur, ref_slot[rp], ob.lambda_for(qp, poc), res[k])
+                k += 1
+            ctx.flush()
+        ctx.sync()
+        for k, (poc, r, rp) in enumerate(passes):
+            oc, om = ob.ref_pass(recon[rp], orig[poc - 1], ob.lambda_for(qp, poc))
+            assert _diff(res[k].cost, res[k].cpmvs, oc, om) == 0, (poc, r)
+        for r_ in res:
+            r_.free()
+    finally:
+        ctx.close()
+
+
 def test_second_device_in_the_same_process(pkg):
     """The CLI's --NumDevices path drives several GPUs from one process: everything that is per-device state (kernel
     attributes, streams, scratch) must be set up for each of them.  Needs two GPUs."""
     import torch
     if torch.cuda.device_count() < 2:
+        # AME_EXPECT_GPUS=N (set by tools/multi_gpu_check.sh on a multi-GPU box): a missing device is a failure there
+        assert int(os.environ.get("AME_EXPECT_GPUS", "1")) < 2, "expected %s GPUs, found %d" % (os.environ["AME_EXPECT_GPUS"], torch.cuda.device_count())
         pytest.skip("needs two GPUs")
     orig, recon = sf.sequences(1, 416, 240, 32, seed=sf.SEED + 5)
     lam = ob.lambda_for(32, 1)
@@ -323,6 +423,42 @@ def _expected_log_bytes(d, W, H, pred, name):
     return ("\n".join(lines) + "\n").encode()
 
 
+def _check_stdout_contract(out, n_passes, n_frames):
+    """The stdout surface the reference's own tooling parses: stage markers in the reference's
+    order (main.cpp call sites of print_timestamp), one START/FINISH EXEC pair per prediction type and pass
+    (main.cpp:764-959; computeEnergy_Affine_NVIDIA_v2.py:83-115 keys on 'START HOST ' and the 'START EXEC ...' lines)
+    and the TIMING RESULTS block of reportTimingResults (main_aux_functions.h:1416-1446)."""
+    import re
+    ts = r" @ \d\d:\d\d:\d\d\.\d\d\d$"
+    stages = ["START HOST", "START READ .csv", "FINISHED READ .csv", "START BUILD KERNELS", "FINISH BUILD KERNELS",
+              "START ALLOCATE MEMORY", "FINISH ALLOCATE MEMORY", "START GPU KERNEL", "FINISH GPU KERNEL", "FINISH HOST"]
+    pos = []
+    for st in stages:
+        m = re.search("^" + re.escape(st) + ts, out, re.M)
+        assert m, st
+        pos.append(m.start())
+    assert pos == sorted(pos)
+    for name in ("FULL 2 CPs", "FULL 3 CPs", "HALF 2 CPs", "HALF 3 CPs"):
+        assert len(re.findall("^START EXEC " + name + ts, out, re.M)) == n_passes, name
+        assert len(re.findall("^FINISH EXEC " + name + ts, out, re.M)) == n_passes, name
+    # per pass: the lambda line, then the four pairs in the reference's order
+    blocks = re.split(r"^POC   \d+  RefIdx  \d+  -> lambda", out, flags=re.M)[1:]
+    assert len(blocks) == n_passes
+    seq = re.findall(r"^(START|FINISH) EXEC (FULL|HALF) ([23]) CPs", blocks[0], re.M)
+    assert seq == [("START", "FULL", "2"), ("FINISH", "FULL", "2"), ("START", "FULL", "3"), ("FINISH", "FULL", "3"),
+                   ("START", "HALF", "2"), ("FINISH", "HALF", "2"), ("START", "HALF", "3"), ("FINISH", "HALF", "3")]
+    assert "TIMING RESULTS (nanoseconds)" in out
+    vals = {}
+    for key in ("FULL_2CP_EXEC", "FULL_3CP_EXEC", "HALF_2CP_EXEC", "HALF_3CP_EXEC", r"TOTAL_EXEC_TIME\(%dx\)" % n_frames, r"OVERALL\(%dx\)" % n_frames):
+        m = re.search("^" + key + r",([0-9.]+)$", out, re.M)
+        assert m, key
+        vals[key] = float(m.group(1))
+    parts = [vals[k] for k in ("FULL_2CP_EXEC", "FULL_3CP_EXEC", "HALF_2CP_EXEC", "HALF_3CP_EXEC")]
+    assert all(v > 0 for v in parts)
+    assert abs(sum(parts) - vals[r"TOTAL_EXEC_TIME\(%dx\)" % n_frames]) <= 1e-6 * sum(parts) + 1.0
+    assert re.search(r"^GPU0_EXEC,[0-9.]+$", out, re.M) and re.search(r"^CSV_INGEST,[0-9.]+ MB/s", out, re.M)
+
+
 def test_cli_logs_are_byte_identical_to_the_reference(pkg, tmp_path):
     """The drop-in CLI on the CSV inputs of a golden run writes the same 40 log files, byte for byte."""
     d = np.load(os.path.join(ROOT, "tests", "golden", "affine_416x240_f3_q32.npz"))
@@ -336,6 +472,7 @@ def test_cli_logs_are_byte_identical_to_the_reference(pkg, tmp_path):
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         assert "START HOST @" in r.stdout and "FINISH HOST @" in r.stdout and "TOTAL_EXEC_TIME(3x)," in r.stdout
         assert "POC   2  RefIdx  1  -> lambda 70.335617" in r.stdout
+        _check_stdout_contract(r.stdout, n_passes=6, n_frames=3)
         files = ame_logs.log_files(prefix)
         assert len(files) == 40
         for pred in range(4):

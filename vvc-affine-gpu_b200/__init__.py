@@ -23,7 +23,7 @@ ROLE_CURRENT, ROLE_REFERENCE = 1, 2
 # every symbol include/affine_me.h declares
 EXPORTS = ("ame_num_ctus", "ame_create", "ame_destroy", "ame_result_len", "ame_set_option", "ame_upload_plane", "ame_upload_plane_ex",
            "ame_search", "ame_search_device", "ame_device_result", "ame_flush", "ame_sync", "ame_last_kernel_ms",
-           "ame_timer_start", "ame_timer_stop", "ame_alloc_host", "ame_free_host", "ame_cu_geometry", "ame_last_error", "ame_version")
+           "ame_timer_start", "ame_timer_stop", "ame_result_block_bytes", "ame_result_bind", "ame_exec_ns", "ame_prepare_plane", "ame_alloc_host", "ame_free_host", "ame_cu_geometry", "ame_last_error", "ame_version")
 
 
 class AmeResult(C.Structure):
@@ -50,6 +50,7 @@ def lib():
         L.ame_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.ame_upload_plane.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ame_upload_plane_ex.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.ame_prepare_plane.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.ame_search.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.POINTER(AmeResult)]
         L.ame_search_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int]
         L.ame_device_result.argtypes = [C.c_void_p, C.c_int, C.POINTER(AmeResult)]
@@ -59,6 +60,10 @@ def lib():
         L.ame_timer_start.argtypes = [C.c_void_p]
         L.ame_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.ame_cu_geometry.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.ame_result_block_bytes.restype = C.c_uint64
+        L.ame_result_block_bytes.argtypes = [C.c_void_p]
+        L.ame_result_bind.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(AmeResult)]
+        L.ame_exec_ns.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
         _lib = L
     return _lib
 
@@ -103,23 +108,38 @@ class PinnedArray:
 
 
 class HostResult:
-    """Pinned destination of one search: cost[p] int64, cpmvs[p] CPMV_DTYPE."""
+    """Pinned destination of one search: cost[p] int64, cpmvs[p] CPMV_DTYPE, in one block laid out like the library's
+    device-side result block (ame_result_bind), so that a search comes back with one device-to-host copy.
+    separate=True allocates eight independent arrays instead (the general ame_result case)."""
 
-    def __init__(self, ctx):
+    def __init__(self, ctx, separate=False):
         self._pins = []
         self.cost, self.cpmvs = [], []
         self.c = AmeResult()
+        if separate:
+            for p in range(4):
+                n = ctx.result_len(p)
+                a = PinnedArray((n,), np.int64)
+                b = PinnedArray((n,), CPMV_DTYPE)
+                self._pins += [a, b]
+                self.cost.append(a.array)
+                self.cpmvs.append(b.array)
+                self.c.cost[p] = a.ptr
+                self.c.cpmvs[p] = b.ptr
+            return
+        nbytes = int(lib().ame_result_block_bytes(ctx.h))
+        blk = PinnedArray((nbytes,), np.uint8)
+        self._pins.append(blk)
+        _check(lib().ame_result_bind(ctx.h, blk.ptr, C.byref(self.c)))
         for p in range(4):
             n = ctx.result_len(p)
-            a = PinnedArray((n,), np.int64)
-            b = PinnedArray((n,), CPMV_DTYPE)
-            self._pins += [a, b]
-            self.cost.append(a.array)
-            self.cpmvs.append(b.array)
-            self.c.cost[p] = a.ptr
-            self.c.cpmvs[p] = b.ptr
+            o = self.c.cost[p] - blk.ptr
+            self.cost.append(blk.array[o:o + 8 * n].view(np.int64))
+            o = self.c.cpmvs[p] - blk.ptr
+            self.cpmvs.append(blk.array[o:o + 28 * n].view(CPMV_DTYPE))
 
     def free(self):
+        self.cost, self.cpmvs = [], []
         for p in self._pins:
             p.free()
         self._pins = []
@@ -159,6 +179,10 @@ class AffineME:
         self._keep.append(arr)
         _check(lib().ame_upload_plane_ex(self.h, slot, arr.ctypes.data, roles))
 
+    def prepare(self, slot, roles):
+        """Re-runs the plane preparation (block order / edge replication + horizontal filter stage) on the resident plane."""
+        _check(lib().ame_prepare_plane(self.h, slot, roles))
+
     def search(self, cur_slot, ref_slot, lam, result, extra_iters=0):
         _check(lib().ame_search(self.h, cur_slot, ref_slot, C.c_float(lam), extra_iters, C.byref(result.c)))
 
@@ -184,6 +208,12 @@ class AffineME:
         ms = C.c_float()
         _check(lib().ame_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+    def exec_ns(self, reset=False):
+        """Device nanoseconds per prediction type (FULL_2CP, FULL_3CP, HALF_2CP, HALF_3CP) since the last reset."""
+        out = (C.c_double * 4)()
+        _check(lib().ame_exec_ns(self.h, out, 1 if reset else 0))
+        return list(out)
 
     def ref_pass(self, ref, cur, lam, extra_iters=0):
         """Convenience: one search on two host planes -> (costs[4], cpmvs[4]) numpy copies."""

@@ -37,10 +37,11 @@ struct Slot {
     uint16_t *raw = nullptr;    // W x H, as uploaded
     uint4 *blk = nullptr;       // current-frame role: the plane in 4x4-block order; allocated on first use
     uint4 *refT = nullptr;      // reference role: 2 x 16 pre-filtered planes; allocated on first use
+    bool hasRaw = false;                  // a plane has been uploaded
     bool hasCur = false, hasRef = false;  // blk / refT match the current contents of raw
 };
 
-struct ResultBlock {  // one per in-flight search, device memory
+struct ResultBlock {  // one per in-flight search, device memory (layout: ame_ctx::resOff / resBytes)
     char *base = nullptr;
     long long *cost[4];
     ame_cpmvs *cpmvs[4];
@@ -63,12 +64,16 @@ struct ame_ctx {
     CuState *dState = nullptr;
     CuAccum *dAccum = nullptr;
     size_t seqSlots = 0;
-    unsigned char *dGoFlag = nullptr;
-    uint4 *dBlockCnt = nullptr, *dBlockOff = nullptr;
-    WorkLists *dWork = nullptr;
-    uint4 *dSmallList = nullptr;
-    uint2 *dBigList = nullptr, *dUpdList = nullptr;
+    WorkLists *dWork = nullptr;               // [kMaxSteps]
+    uint4 *dSmallList = nullptr;              // [2][seqSlots]
+    uint2 *dBigList = nullptr;                // [2][bigCap]
+    unsigned *dGwOut = nullptr;               // [2 * seqSlots]
+    size_t bigCap = 0;
+    unsigned long long *dScan = nullptr;      // 4 x scan_words(seqSlots): ordered compaction of the update / phase kernels
+    Telemetry *dTele = nullptr;
     int *dTab0 = nullptr;
+    bool poisoned = false;                    // a CUDA call failed after work had been issued: only ame_destroy is left
+    std::string poison;
     cudaStream_t stream = nullptr, side = nullptr;  // search kernels (big CUs / small CUs)
     cudaStream_t up = nullptr, down = nullptr;      // plane uploads + preparation / result copies
     cudaEvent_t evUp = nullptr, evKernels = nullptr, evAux = nullptr;
@@ -86,7 +91,28 @@ struct ame_ctx {
     std::vector<Pending> queued;   // searches queued since the last flush
     std::vector<Pending> inflight; // launched, results not yet known complete
     size_t lens[4];
+    size_t resOff[8] = {0}, resBytes = 0;  // byte offsets of cost[0..3], cpmvs[0..3] inside a result block
 };
+
+// A CUDA call that fails after work has been issued leaves streams, scratch and result blocks in an unknown state:
+// the context keeps the error and every later call returns it (ame_destroy is the only way out).
+static int poison(ame_ctx *c, const char *what, cudaError_t e) {
+    c->poisoned = true;
+    c->poison = std::string(what) + ": " + cudaGetErrorString(e);
+    c->queued.clear();
+    c->inflight.clear();
+    return fail(AME_E_CUDA, "%s", c->poison.c_str());
+}
+#define CU_POISON(expr)                                      \
+    do {                                                     \
+        cudaError_t e_ = (expr);                             \
+        if (e_ != cudaSuccess) return poison(c, #expr, e_);  \
+    } while (0)
+#define CHECK_USABLE(c, name)                                                                                       \
+    do {                                                                                                            \
+        if (!(c)) return fail(AME_E_INVALID, name ": ctx is NULL");                                                 \
+        if ((c)->poisoned) return fail(AME_E_CUDA, name ": context unusable after an earlier CUDA error (%s)", (c)->poison.c_str()); \
+    } while (0)
 
 extern "C" {
 
@@ -124,12 +150,11 @@ void ame_destroy(ame_ctx *c) {
     cudaFree(c->dPasses);
     cudaFree(c->dState);
     cudaFree(c->dAccum);
-    cudaFree(c->dUpdList);
+    cudaFree(c->dGwOut);
     cudaFree(c->dTab0);
     cudaFree(c->dWork);
-    cudaFree(c->dGoFlag);
-    cudaFree(c->dBlockCnt);
-    cudaFree(c->dBlockOff);
+    cudaFree(c->dScan);
+    cudaFree(c->dTele);
     cudaFree(c->dSmallList);
     cudaFree(c->dBigList);
     if (c->hPasses) cudaFreeHost(c->hPasses);
@@ -198,15 +223,16 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
     c->planeSetRecs = tiled_plane_set_recs(c->padStride, height + 2 * kPad);
     CTX_TRY(cudaMalloc(&c->padScratch, c->planeElems * sizeof(uint16_t) + 64));
     for (Slot &s : c->slots) CTX_TRY(cudaMalloc(&s.raw, rawBytes));
-    size_t off[8], total = 0;
-    for (int p = 0; p < 4; p++) { off[p] = total; total += (c->lens[p] * sizeof(long long) + 255) & ~(size_t)255; }
-    for (int p = 0; p < 4; p++) { off[4 + p] = total; total += (c->lens[p] * sizeof(ame_cpmvs) + 255) & ~(size_t)255; }
+    size_t total = 0;
+    for (int p = 0; p < 4; p++) { c->resOff[p] = total; total += (c->lens[p] * sizeof(long long) + 255) & ~(size_t)255; }
+    for (int p = 0; p < 4; p++) { c->resOff[4 + p] = total; total += (c->lens[p] * sizeof(ame_cpmvs) + 255) & ~(size_t)255; }
+    c->resBytes = total;
     c->results.resize(max_in_flight);
     for (ResultBlock &r : c->results) {
         CTX_TRY(cudaMalloc(&r.base, total));
         for (int p = 0; p < 4; p++) {
-            r.cost[p] = reinterpret_cast<long long *>(r.base + off[p]);
-            r.cpmvs[p] = reinterpret_cast<ame_cpmvs *>(r.base + off[4 + p]);
+            r.cost[p] = reinterpret_cast<long long *>(r.base + c->resOff[p]);
+            r.cpmvs[p] = reinterpret_cast<ame_cpmvs *>(r.base + c->resOff[4 + p]);
         }
     }
     {   // scratch of one launch sequence: at most min(max_in_flight, kMaxPasses) passes
@@ -215,14 +241,19 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
         CTX_TRY(cudaMalloc(&c->dState, nSlots * sizeof(CuState)));
         c->seqSlots = nSlots;
         CTX_TRY(cudaMalloc(&c->dAccum, 2 * nSlots * sizeof(CuAccum)));
-        CTX_TRY(cudaMalloc(&c->dUpdList, nSlots * sizeof(uint2)));
+        if (nSlots >= 0x7fffffffull) {
+            ame_destroy(c);
+            return fail(AME_E_INVALID, "ame_create: %zu CU slots per launch sequence exceed the 31-bit index of the work lists", nSlots);
+        }
+        c->bigCap = seqPasses * c->nCtus * 9;
+        CTX_TRY(cudaMalloc(&c->dGwOut, 2 * nSlots * sizeof(unsigned)));
         CTX_TRY(cudaMalloc(&c->dTab0, (size_t)kIter0MaxCtas * c->numSMs * (1024 * 45 + 1024) * sizeof(int)));
-        CTX_TRY(cudaMalloc(&c->dWork, sizeof(WorkLists)));
-        CTX_TRY(cudaMalloc(&c->dGoFlag, nSlots));
-        CTX_TRY(cudaMalloc(&c->dBlockCnt, ((nSlots + 127) / 128) * sizeof(uint4)));
-        CTX_TRY(cudaMalloc(&c->dBlockOff, ((nSlots + 127) / 128) * sizeof(uint4)));
-        CTX_TRY(cudaMalloc(&c->dSmallList, nSlots * sizeof(uint4)));
-        CTX_TRY(cudaMalloc(&c->dBigList, seqPasses * c->nCtus * 9 * sizeof(uint2)));
+        CTX_TRY(cudaMalloc(&c->dWork, sizeof(WorkLists) * kMaxSteps));
+        CTX_TRY(cudaMalloc(&c->dScan, 3 * scan_words(nSlots) * sizeof(unsigned long long)));
+        CTX_TRY(cudaMalloc(&c->dTele, sizeof(Telemetry)));
+        CTX_TRY(cudaMemset(c->dTele, 0, sizeof(Telemetry)));
+        CTX_TRY(cudaMalloc(&c->dSmallList, 2 * nSlots * sizeof(uint4)));
+        CTX_TRY(cudaMalloc(&c->dBigList, 2 * c->bigCap * sizeof(uint2)));
     }
     CTX_TRY(cudaMalloc(&c->dPasses, sizeof(PassDesc) * max_in_flight));
     CTX_TRY(cudaHostAlloc(&c->hPasses, sizeof(PassDesc) * max_in_flight, cudaHostAllocDefault));
@@ -255,10 +286,10 @@ int ame_set_option(ame_ctx *c, int option, int value) {
     return fail(AME_E_INVALID, "ame_set_option: unknown option %d", option);
 }
 
-int ame_upload_plane_ex(ame_ctx *c, int slot, const uint16_t *plane, int roles) {
-    if (!c || !plane) return fail(AME_E_INVALID, "ame_upload_plane: NULL argument");
-    if (slot < 0 || slot >= c->numSlots) return fail(AME_E_INVALID, "ame_upload_plane: slot %d out of range", slot);
-    if (!(roles & (AME_ROLE_CURRENT | AME_ROLE_REFERENCE))) return fail(AME_E_INVALID, "ame_upload_plane: no role given");
+// plane == nullptr: the raw plane already in the slot is prepared again (ame_prepare_plane)
+static int upload_or_prepare(ame_ctx *c, int slot, const uint16_t *plane, int roles, const char *name) {
+    if (slot < 0 || slot >= c->numSlots) return fail(AME_E_INVALID, "%s: slot %d out of range", name, slot);
+    if (!(roles & (AME_ROLE_CURRENT | AME_ROLE_REFERENCE))) return fail(AME_E_INVALID, "%s: no role given", name);
     CU_TRY(cudaSetDevice(c->device));
     // Uploads run on their own stream so that they overlap the search kernels of earlier batches.  A slot that
     // queued searches still refer to is launched first; a slot that launched searches may still be reading makes
@@ -269,8 +300,13 @@ int ame_upload_plane_ex(ame_ctx *c, int slot, const uint16_t *plane, int roles) 
     for (const Pending &p : c->inflight) inflightUse |= (p.curSlot == slot || p.refSlot == slot);
     if (inflightUse && c->kernelsRecorded) CU_TRY(cudaStreamWaitEvent(c->up, c->evKernels, 0));
     Slot &s = c->slots[slot];
-    CU_TRY(cudaMemcpyAsync(s.raw, plane, (size_t)c->W * c->H * sizeof(uint16_t), cudaMemcpyHostToDevice, c->up));
-    s.hasRef = s.hasCur = false;
+    if (plane) {
+        CU_TRY(cudaMemcpyAsync(s.raw, plane, (size_t)c->W * c->H * sizeof(uint16_t), cudaMemcpyHostToDevice, c->up));
+        s.hasRaw = true;
+        s.hasRef = s.hasCur = false;
+    } else if (!s.hasRaw) {
+        return fail(AME_E_STATE, "%s: slot %d holds no plane", name, slot);
+    }
     if (roles & AME_ROLE_CURRENT) {
         if (!s.blk) {
             cudaError_t e = cudaMalloc(&s.blk, (size_t)(c->W / 4) * ((c->H + 3) / 4) * 2 * sizeof(uint4));
@@ -294,13 +330,25 @@ int ame_upload_plane_ex(ame_ctx *c, int slot, const uint16_t *plane, int roles) 
     return AME_OK;
 }
 
+int ame_upload_plane_ex(ame_ctx *c, int slot, const uint16_t *plane, int roles) {
+    CHECK_USABLE(c, "ame_upload_plane");
+    if (!plane) return fail(AME_E_INVALID, "ame_upload_plane: NULL argument");
+    return upload_or_prepare(c, slot, plane, roles, "ame_upload_plane");
+}
+
+int ame_prepare_plane(ame_ctx *c, int slot, int roles) {
+    CHECK_USABLE(c, "ame_prepare_plane");
+    return upload_or_prepare(c, slot, nullptr, roles, "ame_prepare_plane");
+}
+
 int ame_upload_plane(ame_ctx *c, int slot, const uint16_t *plane) {
     return ame_upload_plane_ex(c, slot, plane, AME_ROLE_CURRENT | AME_ROLE_REFERENCE);
 }
 
 static int queue_search(ame_ctx *c, int cur_slot, int ref_slot, float lambda, int extra_iters, bool toHost, const ame_result *out, int resultIdx) {
+    CHECK_USABLE(c, "ame_search");
     if (cur_slot < 0 || cur_slot >= c->numSlots || ref_slot < 0 || ref_slot >= c->numSlots) return fail(AME_E_INVALID, "ame_search: slot out of range");
-    if (extra_iters < 0 || extra_iters > 64) return fail(AME_E_INVALID, "ame_search: extra_iters %d out of range", extra_iters);
+    if (extra_iters < 0 || extra_iters > kMaxExtraIter) return fail(AME_E_INVALID, "ame_search: extra_iters %d out of range", extra_iters);
     if (!c->queued.empty() && extra_iters != c->queuedExtra) { int rc = ame_flush(c); if (rc) return rc; }  // one launch sequence = one iteration count
     c->queuedExtra = extra_iters;
     if (!c->slots[ref_slot].hasRef) return fail(AME_E_STATE, "ame_search: slot %d was not uploaded with the reference role", ref_slot);
@@ -352,24 +400,31 @@ int ame_device_result(ame_ctx *c, int result_index, ame_result *out) {
 }
 
 int ame_flush(ame_ctx *c) {
-    if (!c) return fail(AME_E_INVALID, "ame_flush: ctx is NULL");
+    CHECK_USABLE(c, "ame_flush");
     if (c->queued.empty()) return AME_OK;
     CU_TRY(cudaSetDevice(c->device));
     const int n = (int)c->queued.size();
     // Descriptor slots [inflight, inflight + n) are not reused before ame_sync, so the copy can be async.
     const size_t first = c->inflight.size();
-    CU_TRY(cudaMemcpyAsync(c->dPasses + first, c->hPasses + first, sizeof(PassDesc) * n, cudaMemcpyHostToDevice, c->stream));
+    // From here on the searches count as launched: whatever happens, they are never launched a second time.
+    const std::vector<Pending> batch = c->queued;
+    c->inflight.insert(c->inflight.end(), batch.begin(), batch.end());
+    c->queued.clear();
+    CU_POISON(cudaMemcpyAsync(c->dPasses + first, c->hPasses + first, sizeof(PassDesc) * n, cudaMemcpyHostToDevice, c->stream));
     KParams kp;
     kp.W = c->W; kp.H = c->H; kp.ctuCols = c->ctuCols; kp.nCtus = c->nCtus; kp.padStride = c->padStride;
     kp.nStrips = tile_strips(c->padStride);
     kp.cvtRule = c->cvtRule; kp.fusedBacksub = c->fusedBacksub; kp.earlyExit = c->earlyExit;
     kp.slotTab = c->dSlotTab; kp.extraIter = c->queuedExtra;
-    kp.state = c->dState; kp.accum = c->dAccum; kp.accumStride = (unsigned)c->seqSlots; kp.updList = c->dUpdList;
+    kp.state = c->dState; kp.accum = c->dAccum; kp.accumStride = (unsigned)c->seqSlots;
     kp.reuseStart = c->reuseStart; kp.shareFirst = c->shareFirst; kp.tab0 = c->dTab0;
-    kp.goFlag = c->dGoFlag; kp.blockCnt = c->dBlockCnt; kp.blockOff = c->dBlockOff;
-    kp.work = c->dWork; kp.smallList = c->dSmallList; kp.bigList = c->dBigList;
-    CU_TRY(cudaStreamWaitEvent(c->stream, c->evUp, 0));  // every plane uploaded so far is ready (no-op if none)
-    CU_TRY(cudaEventRecord(c->evStart, c->stream));
+    kp.work = c->dWork; kp.tele = c->dTele; kp.gwOut = c->dGwOut;
+    for (int b = 0; b < 2; b++) {
+        kp.smallList[b] = c->dSmallList + (size_t)b * c->seqSlots;
+        kp.bigList[b] = c->dBigList + (size_t)b * c->bigCap;
+    }
+    CU_POISON(cudaStreamWaitEvent(c->stream, c->evUp, 0));  // every plane uploaded so far is ready (no-op if none)
+    CU_POISON(cudaEventRecord(c->evStart, c->stream));
     // One launch sequence per chunk of at most kMaxPasses searches (they share the scratch arrays, in stream order).
     c->lastLaunches = 0;
     static thread_local PassTable pt;
@@ -377,42 +432,78 @@ int ame_flush(ame_ctx *c) {
         const int m = n - k0 < kMaxPasses ? n - k0 : kMaxPasses;
         kp.nPasses = m;
         kp.passes = c->dPasses + first + k0;
+        const size_t words = scan_words((size_t)m * c->nCtus * kSlotsPerCtu);  // the three scan arrays of this sequence, back to back
+        kp.scanEmit[0] = c->dScan; kp.scanEmit[1] = c->dScan + words; kp.scanPhase = c->dScan + 2 * words;
         for (int i = 0; i < m; i++) {
             pt.p[i].curBlk = c->hPasses[first + k0 + i].curBlk;
             pt.p[i].refT = c->hPasses[first + k0 + i].refT;
-            pt.p[i].refRaw = c->slots[c->queued[k0 + i].refSlot].raw;
+            pt.p[i].refRaw = c->slots[batch[k0 + i].refSlot].raw;
         }
-        c->lastLaunches += launch_search(kp, pt, c->numSMs, c->stream, c->side, c->evFork, c->evJoin);
+        CU_POISON(launch_search(kp, pt, c->numSMs, c->stream, c->side, c->evFork, c->evJoin, &c->lastLaunches));
     }
-    CU_TRY(cudaGetLastError());
-    CU_TRY(cudaEventRecord(c->evStop, c->stream));
-    CU_TRY(cudaEventRecord(c->evKernels, c->stream));
+    CU_POISON(cudaGetLastError());
+    CU_POISON(cudaEventRecord(c->evStop, c->stream));
+    CU_POISON(cudaEventRecord(c->evKernels, c->stream));
     c->kernelsRecorded = true;
-    CU_TRY(cudaStreamWaitEvent(c->down, c->evKernels, 0));
+    CU_POISON(cudaStreamWaitEvent(c->down, c->evKernels, 0));
     c->timed = true;
-    for (const Pending &p : c->queued) {
-        if (p.toHost) {
-            const ResultBlock &r = c->results[p.resultIdx];
-            for (int k = 0; k < 4; k++) {
-                CU_TRY(cudaMemcpyAsync(p.host.cost[k], r.cost[k], c->lens[k] * sizeof(long long), cudaMemcpyDeviceToHost, c->down));
-                CU_TRY(cudaMemcpyAsync(p.host.cpmvs[k], r.cpmvs[k], c->lens[k] * sizeof(ame_cpmvs), cudaMemcpyDeviceToHost, c->down));
-            }
+    for (const Pending &p : batch) {
+        if (!p.toHost) continue;
+        const ResultBlock &r = c->results[p.resultIdx];
+        // Host arrays laid out like the device block (ame_result_bind): one copy instead of eight.
+        bool contiguous = true;
+        for (int k = 0; k < 4; k++)
+            contiguous = contiguous && (char *)p.host.cost[k] == (char *)p.host.cost[0] + c->resOff[k] &&
+                         (char *)p.host.cpmvs[k] == (char *)p.host.cost[0] + c->resOff[4 + k];
+        if (contiguous) {
+            CU_POISON(cudaMemcpyAsync(p.host.cost[0], r.base, c->resBytes, cudaMemcpyDeviceToHost, c->down));
+            continue;
         }
-        c->inflight.push_back(p);
+        for (int k = 0; k < 4; k++) {
+            CU_POISON(cudaMemcpyAsync(p.host.cost[k], r.cost[k], c->lens[k] * sizeof(long long), cudaMemcpyDeviceToHost, c->down));
+            CU_POISON(cudaMemcpyAsync(p.host.cpmvs[k], r.cpmvs[k], c->lens[k] * sizeof(ame_cpmvs), cudaMemcpyDeviceToHost, c->down));
+        }
     }
-    c->queued.clear();
     return AME_OK;
 }
 
 int ame_sync(ame_ctx *c) {
-    if (!c) return fail(AME_E_INVALID, "ame_sync: ctx is NULL");
+    CHECK_USABLE(c, "ame_sync");
     int rc = ame_flush(c);
     if (rc) return rc;
     CU_TRY(cudaSetDevice(c->device));
-    CU_TRY(cudaStreamSynchronize(c->up));
-    CU_TRY(cudaStreamSynchronize(c->stream));
-    CU_TRY(cudaStreamSynchronize(c->down));
+    CU_POISON(cudaStreamSynchronize(c->up));
+    CU_POISON(cudaStreamSynchronize(c->stream));
+    CU_POISON(cudaStreamSynchronize(c->down));
     c->inflight.clear();
+    return AME_OK;
+}
+
+uint64_t ame_result_block_bytes(const ame_ctx *c) { return c ? (uint64_t)c->resBytes : 0; }
+
+int ame_result_bind(const ame_ctx *c, void *block, ame_result *out) {
+    if (!c || !block || !out) return fail(AME_E_INVALID, "ame_result_bind: NULL argument");
+    for (int p = 0; p < 4; p++) {
+        out->cost[p] = reinterpret_cast<int64_t *>((char *)block + c->resOff[p]);
+        out->cpmvs[p] = reinterpret_cast<ame_cpmvs *>((char *)block + c->resOff[4 + p]);
+    }
+    return AME_OK;
+}
+
+int ame_exec_ns(ame_ctx *c, double ns[4], int reset) {
+    CHECK_USABLE(c, "ame_exec_ns");
+    if (!ns) return fail(AME_E_INVALID, "ame_exec_ns: NULL argument");
+    if (!c->queued.empty() || !c->inflight.empty()) return fail(AME_E_STATE, "ame_exec_ns: searches in flight; call ame_sync first");
+    CU_TRY(cudaSetDevice(c->device));
+    Telemetry t;
+    CU_TRY(cudaMemcpy(&t, c->dTele, sizeof t, cudaMemcpyDeviceToHost));
+    // ns[nCP - 2] is shared between the aligned and the half-aligned CUs by the 4x4 evaluations each side stood for
+    for (int k = 0; k < 2; k++) {
+        const double full = (double)t.subEvals[k], half = (double)t.subEvals[2 + k], all = full + half;
+        ns[k] = all > 0 ? (double)t.ns[k] * full / all : 0.0;      // AME_FULL_2CP, AME_FULL_3CP
+        ns[2 + k] = all > 0 ? (double)t.ns[k] * half / all : 0.0;  // AME_HALF_2CP, AME_HALF_3CP
+    }
+    if (reset) CU_TRY(cudaMemset(c->dTele, 0, sizeof t));
     return AME_OK;
 }
 
@@ -427,8 +518,12 @@ int ame_last_kernel_ms(ame_ctx *c, float *ms, int *launches) {
 }
 
 int ame_timer_start(ame_ctx *c) {
-    if (!c) return fail(AME_E_INVALID, "ame_timer_start: ctx is NULL");
+    CHECK_USABLE(c, "ame_timer_start");
     CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaEventRecord(c->evAux, c->up));            // the start mark follows everything issued so far on all streams
+    CU_TRY(cudaStreamWaitEvent(c->stream, c->evAux, 0));
+    CU_TRY(cudaEventRecord(c->evAux, c->down));
+    CU_TRY(cudaStreamWaitEvent(c->stream, c->evAux, 0));
     CU_TRY(cudaEventRecord(c->evT0, c->stream));
     CU_TRY(cudaStreamWaitEvent(c->up, c->evT0, 0));    // work issued from now on starts after the start mark
     CU_TRY(cudaStreamWaitEvent(c->down, c->evT0, 0));

@@ -77,10 +77,28 @@ struct PassTable {
     PassPtrs p[kMaxPasses];
 };
 
-// Counters of the work lists (see ame_emit_kernel in ame_kernels.cu).
+// Work lists of one step of a launch sequence.  A step = one evaluation (ame_iter_* / ame_iter0_kernel) + one
+// ame_update_kernel; its lists are written by ame_phase_kernel (first step of a search) or by the ame_emit_kernel
+// launch behind the update of the step before, and every step has its own counters, zeroed once per sequence, so
+// nothing has to be reset between launches.  Entry formats: see "Work lists" in ame_kernels.cu.
 struct WorkLists {
-    unsigned nSmall, nBig, nUpd;    // entries
-    unsigned nextSmall, nextBig, pad[3];  // tickets handed out by the running ame_iter_* launch
+    unsigned nSmall, nBig;                 // entries of the step's two lists
+    unsigned nextSmall, nextBig;           // tickets handed out by the step's ame_iter_* launches
+    unsigned nextChunk;                    // chunk numbers of the ame_emit_kernel launch that reads the step's lists
+    unsigned nextPhaseChunk;               // chunk numbers of the ame_phase_kernel launch that writes the step's lists
+    unsigned pad[2];
+};
+constexpr int kMaxExtraIter = 64;
+constexpr int kMaxSteps = (6 + kMaxExtraIter) + (5 + kMaxExtraIter) + 1;
+
+// Device-side record of where the time of the launch sequences went (ame_exec_ns): %globaltimer at the start of the
+// three ame_phase_kernel launches of a sequence gives the duration of its 2-CP and 3-CP searches; the update kernels
+// count the 4x4 sub-block evaluations per prediction type, by which the host splits the two durations between the
+// aligned and the half-aligned CUs (all four types run fused; main_aux_functions.h:1416-1446 reports them one by one).
+struct Telemetry {
+    unsigned long long mark[3];
+    unsigned long long ns[2];       // accumulated: 2-CP searches, 3-CP searches
+    unsigned long long subEvals[4]; // accumulated: FULL_2CP, FULL_3CP, HALF_2CP, HALF_3CP
 };
 
 constexpr int kIter0MaxCtas = 4;  // resident CTAs per SM ame_iter0_kernel may be built for (AME_ITER0_CTAS)
@@ -95,21 +113,28 @@ struct KParams {
     CuState *state;           // [nPasses * nCtus * kSlotsPerCtu] search state, pass-major
     CuAccum *accum;           // [2][accumStride], same indexing: SATD and moments of the iteration in flight / of the best state
     unsigned accumStride;
-    unsigned char *goFlag;    // same indexing: 1 = the CU is evaluated by the next iteration, 2 = it only takes part in the update
-    uint4 *blockCnt, *blockOff;  // per 128-CU block of the state array: teams (one-warp, one-CTA, update-only) it contributes / offsets
-    WorkLists *work;          // sizes and ticket counters of the lists
-    uint4 *smallList;         // capacity: one entry per CU
-    uint2 *bigList;
-    uint2 *updList;           // CUs that skip the evaluation of the next iteration
+    WorkLists *work;          // [kMaxSteps] sizes and ticket counters of the lists of every step
+    uint4 *smallList[2];      // lists of step s: buffer s & 1; capacity: one entry per CU
+    uint2 *bigList[2];
+    unsigned *gwOut;          // [2 * CUs] per list position of the step: the CU's entry word for the next step, or kNone (ame_update_kernel -> ame_emit_kernel)
+    unsigned long long *scanEmit[2];  // ordered compaction (decoupled look-back) of ame_emit_kernel: one word per 128-CU chunk, buffer s & 1
+    unsigned long long *scanPhase;    // same for ame_phase_kernel
+    Telemetry *tele;
     int *tab0;                // scratch of ame_iter0_kernel: [kIter0MaxCtas * numSMs CTAs][1024 * 45 + 1024]
     int shareFirst;           // 1: the first evaluation of all 2-CP searches is shared per sub-block (ame_iter0_kernel)
     int reuseStart;           // 1: the 3-CP search reuses the evaluation of the best 2-CP state where the motion fields agree
     int extraIter;            // --ExtraGradientIter of this batch (uniform per launch sequence)
 };
 
-// Launches the search kernels (ame_phase_kernel / ame_iter_kernel / ame_update_kernel, one iteration per launch)
-// for all passes (at most kMaxPasses) on `stream`; returns launches made.
-int launch_search(const KParams &kp, const PassTable &pt, int numSMs, cudaStream_t stream, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);
+// Launches the search kernels (ame_phase_kernel / ame_iter_* / ame_update_kernel, one iteration per launch) for all
+// passes (at most kMaxPasses) on `stream`.  Returns cudaSuccess or the first error of a launch / attribute call;
+// *launches += kernels launched.
+cudaError_t launch_search(const KParams &kp, const PassTable &pt, int numSMs, cudaStream_t stream, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join,
+                          int *launches);
+// Number of 128-CU chunks the ordered compaction of a sequence of nSlots CU slots may use: words of each of the three
+// KParams::scan* arrays, which launch_search expects back to back starting at scanEmit[0].
+// (a one-warp CU takes two places of the update kernel's index space, hence 2 x)
+inline size_t scan_words(size_t nSlots) { return (2 * nSlots + 127) / 128 + 1; }
 // dst (padded, stride padStride) <- edge-replicated src (W x H).
 void launch_pad(const uint16_t *src, uint16_t *dst, int W, int H, int padStride, cudaStream_t stream);
 // refT (tiled, tile_record) <- first interpolation stage of the padded plane `pad`, all 16 phases, int16, in

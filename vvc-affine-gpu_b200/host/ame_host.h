@@ -51,7 +51,8 @@ public:
     ~LogWriter();
     bool enabled() const { return !prefix_.empty(); }
     // Appends the rows of one (poc, ref) pass for all four prediction types, in the reference's order.
-    void write_pass(int poc, int ref, const ame_result &res);
+    // Returns the number of rows written.
+    size_t write_pass(int poc, int ref, const ame_result &res);
     void close();
 private:
     struct File { FILE *f = nullptr; std::string name; };
@@ -63,5 +64,6 @@ private:
 };
 
 void print_timestamp(const char *prefix);  // main_aux_functions.h:59-68
+void print_timestamp_at(const char *prefix, double epochSeconds);  // same line for a given instant
 
 }  // namespace host

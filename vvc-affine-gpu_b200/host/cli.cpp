@@ -108,12 +108,20 @@ int check_report_parameters(const Options &o) {
     return errors;
 }
 
+void print_timestamp_at(const char *prefix, double epochSeconds) {
+    const time_t sec = (time_t)epochSeconds;
+    int ms = (int)((epochSeconds - (double)sec) * 1000.0);
+    if (ms < 0) ms = 0;
+    if (ms > 999) ms = 999;
+    struct tm tmv;
+    localtime_r(&sec, &tmv);
+    printf("%s @ %02d:%02d:%02d.%03d\n", prefix, tmv.tm_hour, tmv.tm_min, tmv.tm_sec, ms);
+}
+
 void print_timestamp(const char *prefix) {
     struct timeval tv;
     gettimeofday(&tv, nullptr);
-    struct tm tmv;
-    localtime_r(&tv.tv_sec, &tmv);
-    printf("%s @ %02d:%02d:%02d.%03d\n", prefix, tmv.tm_hour, tmv.tm_min, tmv.tm_sec, (int)(tv.tv_usec / 1000));
+    print_timestamp_at(prefix, (double)tv.tv_sec + (double)tv.tv_usec * 1e-6);
 }
 
 }  // namespace host

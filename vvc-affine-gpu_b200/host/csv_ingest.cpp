@@ -45,8 +45,8 @@ int read_csv_frames(const std::string &path, int nFrames, int W, int H, uint16_t
                 while (p < end && (*p == ' ' || *p == '\t')) p++;
                 unsigned v = 0;
                 bool any = false;
-                while (p < end && *p >= '0' && *p <= '9') { v = v * 10 + (unsigned)(*p - '0'); p++; any = true; }
-                if (!any) { bad++; break; }
+                while (p < end && *p >= '0' && *p <= '9') { v = v < 100000u ? v * 10 + (unsigned)(*p - '0') : v; p++; any = true; }
+                if (!any || v > 65535u) { bad++; break; }  // (not a number / beyond the reference's unsigned short)
                 out[col++] = (uint16_t)v;
                 while (p < end && *p != ',' && *p != '\n') p++;
                 if (p < end && *p == ',') p++;

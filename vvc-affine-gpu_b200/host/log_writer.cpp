@@ -65,8 +65,9 @@ static inline char *put_int(char *p, long long v) {
     return p;
 }
 
-void LogWriter::write_pass(int poc, int ref, const ame_result &res) {
-    if (!enabled()) return;
+size_t LogWriter::write_pass(int poc, int ref, const ame_result &res) {
+    if (!enabled()) return 0;
+    size_t rows = 0;
     static const std::vector<Group> groups[4] = {groups_of(0), groups_of(1), groups_of(2), groups_of(3)};
     for (int pred = 0; pred < 4; pred++) {
         printf("Reporting results POC=%d refIdx=%d PredType=%d\n", poc, ref, pred);
@@ -93,8 +94,10 @@ void LogWriter::write_pass(int poc, int ref, const ame_result &res) {
                 }
             }
             fwrite(buf_.data(), 1, (size_t)(p - buf_.data()), f.f);
+            rows += (size_t)nCtus_ * g.n;
         }
     }
+    return rows;
 }
 
 }  // namespace host

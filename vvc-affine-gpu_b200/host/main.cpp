@@ -27,17 +27,10 @@ struct PassOut {  // pinned result arrays of one (poc, ref) pass
     void *block = nullptr;
 };
 
-static bool alloc_pass(PassOut &p, const size_t lens[4]) {
-    size_t total = 0, off[8];
-    for (int k = 0; k < 4; k++) { off[k] = total; total += (lens[k] * sizeof(int64_t) + 63) & ~(size_t)63; }
-    for (int k = 0; k < 4; k++) { off[4 + k] = total; total += (lens[k] * sizeof(ame_cpmvs) + 63) & ~(size_t)63; }
-    p.block = ame_alloc_host(total);
-    if (!p.block) return false;
-    for (int k = 0; k < 4; k++) {
-        p.res.cost[k] = (int64_t *)((char *)p.block + off[k]);
-        p.res.cpmvs[k] = (ame_cpmvs *)((char *)p.block + off[4 + k]);
-    }
-    return true;
+// One pinned block per pass, laid out like the library's result block: one device-to-host copy per search.
+static bool alloc_pass(PassOut &p, const ame_ctx *ctx) {
+    p.block = ame_alloc_host(ame_result_block_bytes(ctx));
+    return p.block && ame_result_bind(ctx, p.block, &p.res) == AME_OK;
 }
 
 struct Batch {
@@ -45,8 +38,20 @@ struct Batch {
     std::vector<PassOut> passes;           // in (poc, ref) order
     std::vector<std::pair<int, int>> ids;  // (poc, ref)
     bool done = false;
-    double kernelMs = 0;
+    double kernelMs = 0;      // device time of the batch's launch sequence (CUDA events)
+    double execNs[4] = {0, 0, 0, 0};  // the same time per prediction type (ame_exec_ns)
+    double tDone = 0;         // host clock when the results of the batch were complete
+    int device = 0;
 };
+
+static size_t file_size(const std::string &path) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return 0;
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fclose(f);
+    return n > 0 ? (size_t)n : 0;
+}
 
 static double now_s() {
     struct timeval tv;
@@ -87,6 +92,10 @@ int main(int argc, char **argv) {
     }
     const int N = o.nFrames;
     if (N < 1) { std::cout << "  [!] ERROR: FramesToBeEncoded must be positive" << std::endl; return 1; }
+    if (o.extraGradIter < 0 || o.extraGradIter > 64) {
+        std::cout << "  [!] ERROR: ExtraGradientIter must be between 0 and 64" << std::endl;
+        return 1;
+    }
     print_reference_plan(N, o.qp);
 
     // ---- CSV ingest (main.cpp:293-328) ----
@@ -98,6 +107,8 @@ int main(int argc, char **argv) {
         return 1;
     }
     print_timestamp("START READ .csv");
+    const double tRead0 = now_s();
+    size_t csvBytes = 0;
     {
         std::string e1, e2;
         const int threads = std::max(1u, std::thread::hardware_concurrency());
@@ -109,7 +120,9 @@ int main(int argc, char **argv) {
             fprintf(stderr, "%s\n", (r1 ? e1 : e2).c_str());
             return 1;
         }
+        csvBytes = file_size(o.origFile) + file_size(o.refFile);
     }
+    const double readSeconds = now_s() - tRead0;
     print_timestamp("FINISHED READ .csv");
 
     print_timestamp("START BUILD KERNELS");  // kernels are compiled ahead of time; markers kept for the energy scripts
@@ -128,8 +141,6 @@ int main(int argc, char **argv) {
             return 1;
         }
     }
-    size_t lens[4];
-    for (int k = 0; k < 4; k++) lens[k] = (size_t)ame_result_len(ctxs[0], k);
     print_timestamp("FINISH ALLOCATE MEMORY");
 
     const auto lists = reference_lists(N);
@@ -162,7 +173,8 @@ int main(int argc, char **argv) {
             Batch &bt = batches[b];
             bt.passes.resize(bt.ids.size());
             bool ok = true;
-            for (PassOut &p : bt.passes) ok = ok && alloc_pass(p, lens);
+            bt.device = o.deviceIndex + d;
+            for (PassOut &p : bt.passes) ok = ok && alloc_pass(p, ctx);
             // planes: slot i < B holds current frame firstFrame+i; reference POCs get the following slots
             std::map<int, int> refSlot;
             for (int i = 0; ok && i < bt.nFrames; i++) {
@@ -183,6 +195,8 @@ int main(int argc, char **argv) {
             float ms = 0;
             int nl = 0;
             if (ok && ame_last_kernel_ms(ctx, &ms, &nl) == AME_OK) bt.kernelMs = ms;
+            ok = ok && ame_exec_ns(ctx, bt.execNs, 1) == AME_OK;
+            bt.tDone = now_s();
             std::lock_guard<std::mutex> lk(mu);
             if (!ok) {
                 fprintf(stderr, "GPU %d: %s\n", o.deviceIndex + d, ame_last_error());
@@ -197,7 +211,10 @@ int main(int argc, char **argv) {
 
     // ---- writer: consumes batches in POC order (main.cpp:746-748, 980-1003) ----
     LogWriter log(o.cpmvLogFile, W, H);
-    double kernelMs = 0;
+    double kernelMs = 0, execNs[4] = {0, 0, 0, 0}, logSeconds = 0;
+    std::vector<double> devNs(nDev, 0.0);
+    size_t logRows = 0;
+    static const char *kExecName[4] = {"FULL 2 CPs", "FULL 3 CPs", "HALF 2 CPs", "HALF 3 CPs"};
     for (int b = 0; b < nBatches; b++) {
         {
             std::unique_lock<std::mutex> lk(mu);
@@ -206,9 +223,27 @@ int main(int argc, char **argv) {
         }
         Batch &bt = batches[b];
         kernelMs += bt.kernelMs;
+        double batchNs = 0;
+        for (int k = 0; k < 4; k++) { execNs[k] += bt.execNs[k]; batchNs += bt.execNs[k]; }
+        devNs[bt.device - o.deviceIndex] += batchNs;
+        // The searches of a batch run fused (all passes and all four prediction types in one launch sequence), so the
+        // reference's per-launch markers (main.cpp:764-959) are laid out inside the measured interval of the batch:
+        // it ended at tDone and lasted batchNs; every pass gets an equal share, split by the batch's per-type times.
+        const double t0b = bt.tDone - batchNs * 1e-9, perPass = batchNs * 1e-9 / (double)std::max<size_t>(1, bt.ids.size());
         for (size_t k = 0; k < bt.ids.size(); k++) {
             printf("POC   %d  RefIdx  %d  -> lambda %f\n", bt.ids[k].first, bt.ids[k].second, lambda_for(o.qp, bt.ids[k].first));
-            log.write_pass(bt.ids[k].first, bt.ids[k].second, bt.passes[k].res);
+            double t = t0b + perPass * (double)k;
+            for (int pr = 0; pr < 4; pr++) {
+                char name[48];
+                snprintf(name, sizeof name, "START EXEC %s", kExecName[pr]);
+                print_timestamp_at(name, t);
+                t += batchNs > 0 ? perPass * bt.execNs[pr] / batchNs : 0.0;
+                snprintf(name, sizeof name, "FINISH EXEC %s", kExecName[pr]);
+                print_timestamp_at(name, t);
+            }
+            const double tw = now_s();
+            logRows += log.write_pass(bt.ids[k].first, bt.ids[k].second, bt.passes[k].res);
+            logSeconds += now_s() - tw;
             ame_free_host(bt.passes[k].block);
             bt.passes[k].block = nullptr;
         }
@@ -221,13 +256,21 @@ int main(int argc, char **argv) {
     print_timestamp("FINISH GPU KERNEL");
     const double overall = now_s() - t0;
 
-    // reportTimingResults (main_aux_functions.h:1416-1446).  The four prediction types run fused in one pair of
-    // kernels, so only their total is defined; it is printed under the reference's TOTAL_EXEC_TIME key.
+    // reportTimingResults (main_aux_functions.h:1416-1446), same keys.  The per-type figures are device time of the 2-CP /
+    // 3-CP searches split between aligned and half-aligned CUs by evaluated 4x4 blocks (ame_exec_ns); lines after OVERALL
+    // are extensions (per-GPU device time, host-side ingest and log throughput).
     printf("=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=\n");
     printf("TIMING RESULTS (nanoseconds)\n");
-    printf("AFFINE_FUSED_EXEC,%f\n", kernelMs * 1e6);
-    printf("TOTAL_EXEC_TIME(%dx),%f\n", N, kernelMs * 1e6);
+    printf("FULL_2CP_EXEC,%f\n", execNs[0]);
+    printf("FULL_3CP_EXEC,%f\n", execNs[1]);
+    printf("HALF_2CP_EXEC,%f\n", execNs[2]);
+    printf("HALF_3CP_EXEC,%f\n", execNs[3]);
+    printf("TOTAL_EXEC_TIME(%dx),%f\n", N, execNs[0] + execNs[1] + execNs[2] + execNs[3]);
     printf("OVERALL(%dx),%f\n", N, overall);
+    printf("LAUNCH_SEQUENCES_EVENT_TIME,%f\n", kernelMs * 1e6);
+    for (int d = 0; d < nDev; d++) printf("GPU%d_EXEC,%f\n", o.deviceIndex + d, devNs[d]);
+    printf("CSV_INGEST,%.1f MB/s,%.0f samples/s\n", readSeconds > 0 ? csvBytes / readSeconds / 1e6 : 0.0, readSeconds > 0 ? 2.0 * plane * N / readSeconds : 0.0);
+    if (log.enabled()) printf("LOG_WRITE,%.0f rows/s\n", logSeconds > 0 ? logRows / logSeconds : 0.0);
     printf("=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=\n\n");
 
     for (ame_ctx *c : ctxs) ame_destroy(c);
