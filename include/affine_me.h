@@ -89,9 +89,13 @@ enum {
     AME_OPT_REUSE_START = 4,   /* 1 (default) = a 3-CP search whose start state moves every sub-block exactly like the best
                                   2-CP state reuses that state's SATD and normal equations instead of evaluating it again
                                   (results are identical either way) */
-    AME_OPT_SHARE_FIRST = 5    /* 1 (default) = the first evaluation of the 2-CP searches (zero motion for every CU) is
+    AME_OPT_SHARE_FIRST = 5,   /* 1 (default) = the first evaluation of the 2-CP searches (zero motion for every CU) is
                                   computed once per 4x4 block and summed per CU instead of once per CU
                                   (results are identical either way) */
+    AME_OPT_BIG_TMA = 6        /* 1 = CUs of 256..1024 sub-blocks stage the raw search window under their MV field in shared
+                                  memory with TMA (cp.async.bulk.tensor.2d) and run both interpolation stages from there;
+                                  0 = they read the pre-filtered phase planes like the small CUs
+                                  (results are identical either way; the default is the faster one) */
 };
 
 typedef struct ame_ctx ame_ctx;

@@ -159,6 +159,36 @@ def test_reuse_start_is_exact(pkg):
             assert _diff(out[0][0], out[0][1], oc, om) == 0
 
 
+def test_big_cu_tma_window_is_exact(pkg):
+    """AME_OPT_BIG_TMA: CUs of 256..1024 sub-blocks fetch the raw search window under their MV field into shared memory
+    with TMA and run both interpolation stages from there; sub-blocks whose samples fall outside the fetched box use the
+    phase planes.  Same decisions as the phase-plane path and as the oracle: smooth motion (everything inside the
+    window), the large-motion golden (windows that do not fit, clipped MVs at the picture border) and a partial-CTU size."""
+    cases = []
+    orig, recon = sf.sequences(2, 832, 480, 32, seed=sf.SEED + 77)
+    cases.append((recon[0], orig[1], ob.lambda_for(32, 2), None))
+    d = np.load(os.path.join(ROOT, "tests", "golden", "bigmotion_416x240.npz"))
+    cases.append((d["recon"][0], d["orig"][0], ob.lambda_for(int(d["qp"]), 1), d))
+    orig, recon = sf.sequences(1, 1000, 600, 27, seed=sf.SEED + 78)
+    cases.append((recon[0], orig[0], ob.lambda_for(27, 1), None))
+    for ref, cur, lam, gold in cases:
+        H, W = cur.shape
+        out = []
+        for tma in (1, 0):
+            ctx = pkg.AffineME(W, H)
+            try:
+                ctx.set_option(pkg.OPT_BIG_TMA, tma)
+                out.append(ctx.ref_pass(ref, cur, lam))
+            finally:
+                ctx.close()
+        assert _diff(out[0][0], out[0][1], out[1][0], out[1][1]) == 0
+        if gold is not None:
+            assert _diff(out[0][0], out[0][1], [gold["cost_0_%d" % p] for p in range(4)], [gold["cpmv_0_%d" % p] for p in range(4)]) == 0
+        else:
+            oc, om = ob.ref_pass(ref, cur, lam)
+            assert _diff(out[0][0], out[0][1], oc, om) == 0
+
+
 def test_share_first_is_exact(pkg):
     """AME_OPT_SHARE_FIRST: evaluating the zero-motion start of all 2-CP searches once per 4x4 block (nine border-ring
     cases) and summing per CU must give the decisions of the per-CU evaluation; 416x240 has partial CTUs on both axes."""
@@ -483,3 +513,34 @@ def test_cli_logs_are_byte_identical_to_the_reference(pkg, tmp_path):
             for nm in names:
                 got = open(prefix + ame_logs.PRED_TAGS[pred] + nm + ".csv", "rb").read()
                 assert got == _expected_log_bytes(d, W, H, pred, nm), (pred, nm)
+
+
+REF_ON_LIB = os.path.join(ROOT, "oracle", "_ref", "affine_ref_ame")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ON_LIB), reason="oracle/_ref/affine_ref_ame not built (needs /root/reference at build time: make -C oracle ref)")
+def test_unmodified_reference_host_runs_on_the_library(pkg, tmp_path):
+    """The drop-in boundary, compiled: the UNMODIFIED reference host program (/root/reference/main.cpp, built by
+    oracle/Makefile) linked against oracle/shim/cl_ame_shim.cpp, which binds its 14 x clSetKernelArg +
+    clEnqueueNDRangeKernel to ame_upload_plane_ex / ame_search / ame_sync of libaffine_me.so.  Its own CSV reader,
+    reference-list rotation, lambda schedule and log writer run as they are; the 40 log files must be the bytes the
+    reference wrote with its OpenCL kernels on a B200 (golden fixture)."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "affine_416x240_f3_q32.npz"))
+    n, H, W = d["orig"].shape
+    sf.write_csv(str(tmp_path / "orig.csv"), d["orig"])
+    sf.write_csv(str(tmp_path / "recon.csv"), d["recon"])
+    prefix = str(tmp_path / "reflog")
+    r = subprocess.run([REF_ON_LIB, "-f", str(n), "-s", "%dx%d" % (W, H), "-q", "32", "-o", str(tmp_path / "orig.csv"), "-r", str(tmp_path / "recon.csv"),
+                        "-l", prefix], capture_output=True, text=True, cwd=os.path.dirname(REF_ON_LIB), timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "COMPUTING ON GPU 0" in r.stdout and "TOTAL_EXEC_TIME(3x)," in r.stdout
+    files = ame_logs.log_files(prefix)
+    assert len(files) == 40
+    for pred in range(4):
+        names = []
+        for (w, h, _) in ame_logs.groups(pred):
+            if "%dx%d" % (w, h) not in names:
+                names.append("%dx%d" % (w, h))
+        for nm in names:
+            got = open(prefix + ame_logs.PRED_TAGS[pred] + nm + ".csv", "rb").read()
+            assert got == _expected_log_bytes(d, W, H, pred, nm), (pred, nm)

@@ -36,6 +36,9 @@ sf.write_csv(os.path.join(tmp, "r8.csv"), r8)
 for k in (1, ndev):
     r = subprocess.run([CLI, "-f", "8", "-s", "1920x1080", "-q", "32", "-o", os.path.join(tmp, "o8.csv"), "-r", os.path.join(tmp, "r8.csv"),
                         "--NumDevices", str(k)], capture_output=True, text=True)
-    lines = [l for l in r.stdout.splitlines() if "READ .csv" in l or "EXEC" in l or "OVERALL" in l]
-    print("--NumDevices %d:" % k, " | ".join(lines))
+    lines = [l for l in r.stdout.splitlines() if "READ .csv" in l or ("_EXEC" in l) or "OVERALL" in l or "CSV_INGEST" in l]
+    print("--NumDevices %d: rc=%d" % (k, r.returncode), " | ".join(lines))
+    if r.returncode != 0 or sum(1 for l in lines if l.startswith("GPU") and "_EXEC," in l) != k:
+        print(r.stdout[-1500:], r.stderr[-1500:])
+        sys.exit("1080p CLI run with --NumDevices %d failed or lacks its per-GPU lines" % k)
 sys.exit(1 if bad else 0)

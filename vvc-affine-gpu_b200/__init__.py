@@ -17,7 +17,7 @@ CLI_PATH = os.path.join(HERE, "bin", "affine_b200")
 PRED_NAMES = ("FULL_2CP", "FULL_3CP", "HALF_2CP", "HALF_3CP")
 CPMV_DTYPE = np.dtype([("nCPs", "<i4"), ("LTx", "<i4"), ("LTy", "<i4"), ("RTx", "<i4"),
                        ("RTy", "<i4"), ("LBx", "<i4"), ("LBy", "<i4")])
-OPT_CVT_RULE, OPT_FUSED_BACKSUB, OPT_EARLY_EXIT, OPT_REUSE_START, OPT_SHARE_FIRST = 1, 2, 3, 4, 5
+OPT_CVT_RULE, OPT_FUSED_BACKSUB, OPT_EARLY_EXIT, OPT_REUSE_START, OPT_SHARE_FIRST, OPT_BIG_TMA = 1, 2, 3, 4, 5, 6
 ROLE_CURRENT, ROLE_REFERENCE = 1, 2
 
 # every symbol include/affine_me.h declares
@@ -154,6 +154,8 @@ class AffineME:
         _check(lib().ame_create(C.byref(h), device, width, height, num_slots, max_in_flight))
         self.h = h
         self._keep = []
+        if os.environ.get("AME_BIG_TMA", "") != "":  # development A/B switch (tools/, bench.py)
+            self.set_option(OPT_BIG_TMA, int(os.environ["AME_BIG_TMA"]))
 
     def close(self):
         if self.h:

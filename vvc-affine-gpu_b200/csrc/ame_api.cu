@@ -1,12 +1,14 @@
 // C-ABI layer of include/affine_me.h: context, frame slots, queued searches, result copies.
 // Replaces the OpenCL buffer / argument / enqueue / readback code of the reference
 // (/root/reference/main.cpp:484-552, 746-966; main_aux_functions.h:335-383).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -33,10 +35,15 @@ static int fail(int code, const char *fmt, ...) {
         if (e_ != cudaSuccess) return fail(AME_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
     } while (0)
 
+#ifndef AME_BIG_TMA_DEFAULT
+#define AME_BIG_TMA_DEFAULT 1
+#endif
+
 struct Slot {
     uint16_t *raw = nullptr;    // W x H, as uploaded
     uint4 *blk = nullptr;       // current-frame role: the plane in 4x4-block order; allocated on first use
     uint4 *refT = nullptr;      // reference role: 2 x 16 pre-filtered planes; allocated on first use
+    uint16_t *refPad = nullptr; // reference role: the edge-replicated plane (input of the phase filter; TMA source of the big-CU windows)
     bool hasRaw = false;                  // a plane has been uploaded
     bool hasCur = false, hasRef = false;  // blk / refT match the current contents of raw
 };
@@ -56,7 +63,8 @@ struct Pending {
 struct ame_ctx {
     int device = 0, W = 0, H = 0, nCtus = 0, ctuCols = 0, padStride = 0;
     int numSlots = 0, maxInFlight = 0;
-    int cvtRule = 1, fusedBacksub = 1, earlyExit = 1, reuseStart = 1, shareFirst = 1;
+    int cvtRule = 1, fusedBacksub = 1, earlyExit = 1, reuseStart = 1, shareFirst = 1, bigTma = AME_BIG_TMA_DEFAULT;
+    unsigned char *dTmaps = nullptr;  // [numSlots][4] CUtensorMap over refPad (boxes of tma_box(i) x tma_box(j) samples)
     int queuedExtra = 0;
     int numSMs = 0;
     uint32_t *dSlotTab = nullptr;
@@ -81,7 +89,6 @@ struct ame_ctx {
     cudaEvent_t evStart = nullptr, evStop = nullptr, evFork = nullptr, evJoin = nullptr, evT0 = nullptr, evT1 = nullptr;
     bool timed = false;
     int lastLaunches = 0;
-    uint16_t *padScratch = nullptr;  // (W + 2*kPad) x (H + 2*kPad) edge-replicated plane, input of the phase filter
     size_t planeElems = 0;  // samples of the padded plane
     size_t planeSetRecs = 0;  // 16-byte records of the 2 x 16 tiled pre-filtered planes of one reference (refT)
     std::vector<Slot> slots;
@@ -143,8 +150,8 @@ void ame_destroy(ame_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (cudaStream_t s : {c->up, c->stream, c->side, c->down}) if (s) cudaStreamSynchronize(s);
-    for (Slot &s : c->slots) { cudaFree(s.raw); cudaFree(s.blk); cudaFree(s.refT); }
-    cudaFree(c->padScratch);
+    for (Slot &s : c->slots) { cudaFree(s.raw); cudaFree(s.blk); cudaFree(s.refT); cudaFree(s.refPad); }
+    cudaFree(c->dTmaps);
     for (ResultBlock &r : c->results) cudaFree(r.base);
     cudaFree(c->dSlotTab);
     cudaFree(c->dPasses);
@@ -221,7 +228,7 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
     const size_t rawBytes = (size_t)width * height * sizeof(uint16_t);
     c->planeElems = (size_t)c->padStride * (height + 2 * kPad);
     c->planeSetRecs = tiled_plane_set_recs(c->padStride, height + 2 * kPad);
-    CTX_TRY(cudaMalloc(&c->padScratch, c->planeElems * sizeof(uint16_t) + 64));
+    CTX_TRY(cudaMalloc(&c->dTmaps, (size_t)num_slots * 4 * sizeof(CUtensorMap)));
     for (Slot &s : c->slots) CTX_TRY(cudaMalloc(&s.raw, rawBytes));
     size_t total = 0;
     for (int p = 0; p < 4; p++) { c->resOff[p] = total; total += (c->lens[p] * sizeof(long long) + 255) & ~(size_t)255; }
@@ -282,8 +289,37 @@ int ame_set_option(ame_ctx *c, int option, int value) {
         case AME_OPT_EARLY_EXIT: c->earlyExit = value ? 1 : 0; return AME_OK;
         case AME_OPT_REUSE_START: c->reuseStart = value ? 1 : 0; return AME_OK;
         case AME_OPT_SHARE_FIRST: c->shareFirst = value ? 1 : 0; return AME_OK;
+        case AME_OPT_BIG_TMA: c->bigTma = value ? 1 : 0; return AME_OK;
     }
     return fail(AME_E_INVALID, "ame_set_option: unknown option %d", option);
+}
+
+// The four tensor maps of a slot's edge-replicated plane (2-D, uint16, row pitch padStride; boxes of tma_box(i) x
+// tma_box(j) samples, no swizzle) go to device memory, from where ame_iter_big<true> hands them to cp.async.bulk.tensor.
+// cuTensorMapEncodeTiled is the one driver-API call of the library; it is looked up through the runtime.
+static int encode_tensor_maps(ame_ctx *c, int slot) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return fail(AME_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    CUtensorMap maps[4];
+    const cuuint64_t dims[2] = {(cuuint64_t)c->padStride, (cuuint64_t)(c->H + 2 * kPad)};
+    const cuuint64_t strides[1] = {(cuuint64_t)c->padStride * sizeof(uint16_t)};
+    const cuuint32_t elemStrides[2] = {1, 1};
+    for (int k = 0; k < 4; k++) {
+        const cuuint32_t box[2] = {(cuuint32_t)tma_box((k >> 1) != 0), (cuuint32_t)tma_box((k & 1) != 0)};
+        const CUresult r = encode(&maps[k], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, c->slots[slot].refPad, dims, strides, box, elemStrides, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(AME_E_CUDA, "cuTensorMapEncodeTiled (slot %d, box %d x %d): error %d", slot, (int)box[0], (int)box[1], (int)r);
+    }
+    CU_TRY(cudaMemcpyAsync(c->dTmaps + (size_t)slot * sizeof maps, maps, sizeof maps, cudaMemcpyHostToDevice, c->up));  // (pageable source: staged before the call returns)
+    return AME_OK;
 }
 
 // plane == nullptr: the raw plane already in the slot is prepared again (ame_prepare_plane)
@@ -319,10 +355,13 @@ static int upload_or_prepare(ame_ctx *c, int slot, const uint16_t *plane, int ro
     if (roles & AME_ROLE_REFERENCE) {
         if (!s.refT) {
             cudaError_t e = cudaMalloc(&s.refT, c->planeSetRecs * sizeof(uint4));
+            if (e == cudaSuccess) e = cudaMalloc(&s.refPad, c->planeElems * sizeof(uint16_t) + 64);
             if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? AME_E_NOMEM : AME_E_CUDA, "pre-filtered planes of slot %d: %s", slot, cudaGetErrorString(e));
+            int rc = encode_tensor_maps(c, slot);
+            if (rc) return rc;
         }
-        launch_pad(s.raw, c->padScratch, c->W, c->H, c->padStride, c->up);
-        launch_phase_planes(c->padScratch, s.refT, c->W, c->H, c->padStride, c->up);
+        launch_pad(s.raw, s.refPad, c->W, c->H, c->padStride, c->up);
+        launch_phase_planes(s.refPad, s.refT, c->W, c->H, c->padStride, c->up);
         CU_TRY(cudaGetLastError());
         s.hasRef = true;
     }
@@ -417,7 +456,7 @@ int ame_flush(ame_ctx *c) {
     kp.cvtRule = c->cvtRule; kp.fusedBacksub = c->fusedBacksub; kp.earlyExit = c->earlyExit;
     kp.slotTab = c->dSlotTab; kp.extraIter = c->queuedExtra;
     kp.state = c->dState; kp.accum = c->dAccum; kp.accumStride = (unsigned)c->seqSlots;
-    kp.reuseStart = c->reuseStart; kp.shareFirst = c->shareFirst; kp.tab0 = c->dTab0;
+    kp.reuseStart = c->reuseStart; kp.shareFirst = c->shareFirst; kp.tab0 = c->dTab0; kp.bigTma = c->bigTma;
     kp.work = c->dWork; kp.tele = c->dTele; kp.gwOut = c->dGwOut;
     for (int b = 0; b < 2; b++) {
         kp.smallList[b] = c->dSmallList + (size_t)b * c->seqSlots;
@@ -438,6 +477,7 @@ int ame_flush(ame_ctx *c) {
             pt.p[i].curBlk = c->hPasses[first + k0 + i].curBlk;
             pt.p[i].refT = c->hPasses[first + k0 + i].refT;
             pt.p[i].refRaw = c->slots[batch[k0 + i].refSlot].raw;
+            pt.p[i].tmap = c->dTmaps + (size_t)batch[k0 + i].refSlot * 4 * sizeof(CUtensorMap);
         }
         CU_POISON(launch_search(kp, pt, c->numSMs, c->stream, c->side, c->evFork, c->evJoin, &c->lastLaunches));
     }

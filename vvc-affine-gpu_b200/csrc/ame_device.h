@@ -72,6 +72,8 @@ struct PassPtrs {
     const uint4 *curBlk;
     const uint4 *refT;
     const uint16_t *refRaw;  // the reference plane as uploaded (W x H), for ame_iter0_kernel
+    const void *tmap;        // four CUtensorMap (128 bytes each, device memory) over the edge-replicated reference plane
+                             // (padStride x (H + 2*kPad) uint16): boxes of tma_box(i) x tma_box(j) samples at index 2*i + j, for ame_iter_big<true>
 };
 struct PassTable {
     PassPtrs p[kMaxPasses];
@@ -124,7 +126,11 @@ struct KParams {
     int shareFirst;           // 1: the first evaluation of all 2-CP searches is shared per sub-block (ame_iter0_kernel)
     int reuseStart;           // 1: the 3-CP search reuses the evaluation of the best 2-CP state where the motion fields agree
     int extraIter;            // --ExtraGradientIter of this batch (uniform per launch sequence)
+    int bigTma;               // 1: big CUs stage their search window in shared memory with TMA (ame_iter_big<true>)
 };
+// box extents (samples) of the tensor maps of a reference plane, for a CU extent of 64 / 128: see ame_iter_big<true>
+constexpr int kTmaBoxSmall = 96, kTmaBoxBig = 160;
+__host__ __device__ constexpr int tma_box(bool extent128) { return extent128 ? kTmaBoxBig : kTmaBoxSmall; }
 
 // Launches the search kernels (ame_phase_kernel / ame_iter_* / ame_update_kernel, one iteration per launch) for all
 // passes (at most kMaxPasses) on `stream`.  Returns cudaSuccess or the first error of a launch / attribute call;

@@ -131,7 +131,8 @@ int main(int argc, char **argv) {
     // ---- contexts, one per GPU ----
     print_timestamp("START ALLOCATE MEMORY");
     const int nDev = std::max(1, o.numDevices);
-    const int B = std::max(1, std::min(o.batchFrames, N));
+    // frames per batch: --BatchFrames, but never so many that a GPU is left without a batch
+    const int B = std::max(1, std::min(o.batchFrames, (N + nDev - 1) / nDev));
     const int slots = 2 * B + 8;  // B current planes + up to B+3 reference planes (+ slack)
     const int inflight = 4 * B;
     std::vector<ame_ctx *> ctxs(nDev, nullptr);
