@@ -345,15 +345,17 @@ def run_b200(args, rank, world, local_rank):
     my_passes_per_step = sum(first_pass_of[f1] - first_pass_of[f0] for s in sequences for (f0, f1) in s)
     max_seq_passes = max(sum(first_pass_of[f1] - first_pass_of[f0] for (f0, f1) in s) for s in sequences)
 
-    # slots: 0..n-1 = original frames (poc-1), n..2n-1 = reconstructed frames 0..n-1
-    ctx = pkg.AffineME(w, h, device=local_rank, num_slots=2 * n_frames, max_in_flight=max_seq_passes)
+    # slots: 0..n-1 = original frames (poc-1), n..2n-1 = reconstructed frames 0..n-1 (sharded end-to-end path: one such
+    # set per sequence of a group)
+    E2E_GROUP = 2 if sharded else 1
+    ctx = pkg.AffineME(w, h, device=local_rank, num_slots=2 * n_frames * E2E_GROUP, max_in_flight=max_seq_passes * E2E_GROUP)
     pin_orig = pkg.PinnedArray(orig.shape, np.uint16)
     pin_orig.array[...] = orig
     pin_recon = {}
     for qp in qps:
         pin_recon[qp] = pkg.PinnedArray(recon[qp].shape, np.uint16)
         pin_recon[qp].array[...] = recon[qp]
-    host_res = [pkg.HostResult(ctx) for _ in range(max_seq_passes)]
+    host_res = [pkg.HostResult(ctx) for _ in range(max_seq_passes * E2E_GROUP)]
 
     def upload_all(qp):
         for f in range(n_frames):
@@ -414,20 +416,27 @@ def run_b200(args, rank, world, local_rank):
         t0 = time.perf_counter()
         ctx.timer_start()
         if sharded:
-            # every sequence: upload the planes its blocks need, search, read back; sequences pipeline through the streams
-            for seq in sequences:
-                need_cur = sorted({f for (f0, f1) in seq for f in range(f0, f1)})
-                need_ref = sorted({passes[k][2] for k in seq_passes(seq)})
-                for f in need_cur:
-                    ctx.upload(f, pin_orig.array[f], pkg.ROLE_CURRENT)
-                for f in need_ref:
-                    ctx.upload(n_frames + f, pin_recon[qp].array[f], pkg.ROLE_REFERENCE)
-                for i, k in enumerate(seq_passes(seq)):
-                    poc, r, refpoc = passes[k]
-                    ctx.search(poc - 1, n_frames + refpoc, lambda_for(qp, poc), host_res[i])
-                ctx.sync()   # host result buffers are reused by the next sequence
-                if want is not None and want in seq_passes(seq) and not any(c[0] == qp and c[1] == want for c in checks):
-                    keep_for_check(step, qp, want, host_res[seq_passes(seq).index(want)])
+            # every sequence: upload the planes its blocks need, search, read back.  E2E_GROUP sequences are launched
+            # before the host waits, each with its own set of plane slots, result blocks and host buffers: the uploads of
+            # the second and the result copies of the first run beside the kernels (one ame_sync waits for everything).
+            for s0 in range(0, len(sequences), E2E_GROUP):
+                group = sequences[s0:s0 + E2E_GROUP]
+                for gi, seq in enumerate(group):
+                    off, slot0 = gi * max_seq_passes, gi * 2 * n_frames
+                    need_cur = sorted({f for (f0, f1) in seq for f in range(f0, f1)})
+                    need_ref = sorted({passes[k][2] for k in seq_passes(seq)})
+                    for f in need_cur:
+                        ctx.upload(slot0 + f, pin_orig.array[f], pkg.ROLE_CURRENT)
+                    for f in need_ref:
+                        ctx.upload(slot0 + n_frames + f, pin_recon[qp].array[f], pkg.ROLE_REFERENCE)
+                    for i, k in enumerate(seq_passes(seq)):
+                        poc, r, refpoc = passes[k]
+                        ctx.search(slot0 + poc - 1, slot0 + n_frames + refpoc, lambda_for(qp, poc), host_res[off + i])
+                    ctx.flush()
+                ctx.sync()   # host result buffers and slots are reused by the next group
+                for gi, seq in enumerate(group):
+                    if want is not None and want in seq_passes(seq) and not any(c[0] == qp and c[1] == want for c in checks):
+                        keep_for_check(step, qp, want, host_res[gi * max_seq_passes + seq_passes(seq).index(want)])
         else:
             k = 0
             f0 = 0

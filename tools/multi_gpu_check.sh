@@ -17,5 +17,9 @@ export AME_EXPECT_GPUS=$N
     echo "== bench.py --config shard4096 --gpus $N (torchrun)"
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --config shard4096 --steps 1 --warmup 1 2>&1 | grep -E "^\{|rror|PARITY" | tail -3
   fi
+  if [ "${3:-}" = "4k" ]; then
+    echo "== bench.py --config 4k --gpus $N (torchrun)"
+    timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --config 4k --steps 1 --warmup 1 2>&1 | grep -E "^\{|rror|PARITY" | tail -3
+  fi
 } > $O 2>&1
 tail -30 $O

@@ -1,6 +1,8 @@
 """Joins an ncu report's per-SASS-instruction counters with nvdisasm line info of the same kernel build and
 prints dynamic instruction counts / stall samples per source function.
-usage: ncu_by_function.py report.ncu-rep [kernel# in the report] [kernel function name, default ame_iter_small]"""
+usage: ncu_by_function.py report.ncu-rep [kernel# in the report] [kernel function name, default ame_iter_small]
+The name selects the .text section by substring: give the mangled instance of a template (ame_update_kernelILi3E,
+ame_iter_bigILb1E), or the listing holds the instructions of all its instances."""
 import bisect, collections, csv, io, os, re, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
