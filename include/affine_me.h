@@ -92,10 +92,13 @@ enum {
     AME_OPT_SHARE_FIRST = 5,   /* 1 (default) = the first evaluation of the 2-CP searches (zero motion for every CU) is
                                   computed once per 4x4 block and summed per CU instead of once per CU
                                   (results are identical either way) */
-    AME_OPT_BIG_TMA = 6        /* 1 = CUs of 256..1024 sub-blocks stage the raw search window under their MV field in shared
+    AME_OPT_BIG_TMA = 6,       /* 1 = CUs of 256..1024 sub-blocks stage the raw search window under their MV field in shared
                                   memory with TMA (cp.async.bulk.tensor.2d) and run both interpolation stages from there;
                                   0 = they read the pre-filtered phase planes like the small CUs
                                   (results are identical either way; the default is the faster one) */
+    AME_OPT_GROUP_BY_REF = 7   /* 1 (default) = the searches of a launch sequence that share a reference plane (the long-term
+                                  references of main.cpp:591-707 are searched by many frames) are worked on CTU by CTU side
+                                  by side, so that they share the plane's rows in L2; 0 = search after search */
 };
 
 typedef struct ame_ctx ame_ctx;

@@ -319,6 +319,42 @@ def test_twelve_frame_sequence_matches_oracle(pkg):
         ctx.close()
 
 
+def test_group_by_reference_is_exact(pkg):
+    """AME_OPT_GROUP_BY_REF only changes the order in which the searches of a launch sequence are worked on (the passes
+    that share a reference plane CTU by CTU side by side): every search of a 12-frame sequence must give the same
+    decisions in both orders, with the phase-plane and with the TMA-window big-CU path."""
+    W, H, n, qp = 416, 240, 12, 32
+    orig, recon = sf.sequences(n, W, H, qp, seed=sf.SEED + 97)
+    passes = _sequence_passes(n)
+    out = {}
+    for group, tma in ((1, 1), (0, 1), (1, 0)):
+        ctx = pkg.AffineME(W, H, num_slots=2 * n, max_in_flight=len(passes))
+        try:
+            ctx.set_option(pkg.OPT_GROUP_BY_REF, group)
+            ctx.set_option(pkg.OPT_BIG_TMA, tma)
+            for f in range(n):
+                ctx.upload(f, orig[f], pkg.ROLE_CURRENT)
+                ctx.upload(n + f, recon[f], pkg.ROLE_REFERENCE)
+            res = [pkg.HostResult(ctx) for _ in passes]
+            for k, (poc, r, rp) in enumerate(passes):
+                ctx.search(poc - 1, n + rp, ob.lambda_for(qp, poc), res[k])
+            ctx.sync()
+            out[(group, tma)] = [([c.copy() for c in r_.cost], [m.copy() for m in r_.cpmvs]) for r_ in res]
+            for r_ in res:
+                r_.free()
+        finally:
+            ctx.close()
+    for k in range(len(passes)):
+        a = out[(1, 1)][k]
+        for other in ((0, 1), (1, 0)):
+            b = out[other][k]
+            assert _diff(a[0], a[1], b[0], b[1]) == 0, (k, other)
+    for k in (0, 17, 41):   # and against the oracle for a short-term and two long-term passes
+        poc, r, rp = passes[k]
+        oc, om = ob.ref_pass(recon[rp], orig[poc - 1], ob.lambda_for(qp, poc))
+        assert _diff(out[(1, 1)][k][0], out[(1, 1)][k][1], oc, om) == 0, k
+
+
 def test_overlapped_pipeline_matches_oracle(pkg):
     """The end-to-end pipeline of bench.py / the CLI: uploads and ame_flush in chunks WITHOUT ame_sync in between
     (descriptor slots at an offset, uploads running beside kernels in flight), with so few plane slots that a slot

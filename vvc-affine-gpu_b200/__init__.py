@@ -17,7 +17,7 @@ CLI_PATH = os.path.join(HERE, "bin", "affine_b200")
 PRED_NAMES = ("FULL_2CP", "FULL_3CP", "HALF_2CP", "HALF_3CP")
 CPMV_DTYPE = np.dtype([("nCPs", "<i4"), ("LTx", "<i4"), ("LTy", "<i4"), ("RTx", "<i4"),
                        ("RTy", "<i4"), ("LBx", "<i4"), ("LBy", "<i4")])
-OPT_CVT_RULE, OPT_FUSED_BACKSUB, OPT_EARLY_EXIT, OPT_REUSE_START, OPT_SHARE_FIRST, OPT_BIG_TMA = 1, 2, 3, 4, 5, 6
+OPT_CVT_RULE, OPT_FUSED_BACKSUB, OPT_EARLY_EXIT, OPT_REUSE_START, OPT_SHARE_FIRST, OPT_BIG_TMA, OPT_GROUP_BY_REF = 1, 2, 3, 4, 5, 6, 7
 ROLE_CURRENT, ROLE_REFERENCE = 1, 2
 
 # every symbol include/affine_me.h declares
@@ -156,6 +156,8 @@ class AffineME:
         self._keep = []
         if os.environ.get("AME_BIG_TMA", "") != "":  # development A/B switch (tools/, bench.py)
             self.set_option(OPT_BIG_TMA, int(os.environ["AME_BIG_TMA"]))
+        if os.environ.get("AME_GROUP_BY_REF", "") != "":
+            self.set_option(OPT_GROUP_BY_REF, int(os.environ["AME_GROUP_BY_REF"]))
 
     def close(self):
         if self.h:

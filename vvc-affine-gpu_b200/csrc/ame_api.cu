@@ -76,6 +76,8 @@ struct ame_ctx {
     uint4 *dSmallList = nullptr;              // [2][seqSlots]
     uint2 *dBigList = nullptr;                // [2][bigCap]
     unsigned *dGwOut = nullptr;               // [2 * seqSlots]
+    unsigned *dRowTab = nullptr;              // [seqPasses * nCtus] (pass, CTU) of every row of the state array, per launch sequence
+    int groupByRef = 1;                       // rows ordered (reference plane, CTU, pass) instead of (pass, CTU)
     size_t bigCap = 0;
     unsigned long long *dScan = nullptr;      // 4 x scan_words(seqSlots): ordered compaction of the update / phase kernels
     Telemetry *dTele = nullptr;
@@ -158,6 +160,7 @@ void ame_destroy(ame_ctx *c) {
     cudaFree(c->dState);
     cudaFree(c->dAccum);
     cudaFree(c->dGwOut);
+    cudaFree(c->dRowTab);
     cudaFree(c->dTab0);
     cudaFree(c->dWork);
     cudaFree(c->dScan);
@@ -254,6 +257,7 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
         }
         c->bigCap = seqPasses * c->nCtus * 9;
         CTX_TRY(cudaMalloc(&c->dGwOut, 2 * nSlots * sizeof(unsigned)));
+        CTX_TRY(cudaMalloc(&c->dRowTab, seqPasses * c->nCtus * sizeof(unsigned)));
         CTX_TRY(cudaMalloc(&c->dTab0, (size_t)kIter0MaxCtas * c->numSMs * (1024 * 45 + 1024) * sizeof(int)));
         CTX_TRY(cudaMalloc(&c->dWork, sizeof(WorkLists) * kMaxSteps));
         CTX_TRY(cudaMalloc(&c->dScan, 3 * scan_words(nSlots) * sizeof(unsigned long long)));
@@ -290,6 +294,7 @@ int ame_set_option(ame_ctx *c, int option, int value) {
         case AME_OPT_REUSE_START: c->reuseStart = value ? 1 : 0; return AME_OK;
         case AME_OPT_SHARE_FIRST: c->shareFirst = value ? 1 : 0; return AME_OK;
         case AME_OPT_BIG_TMA: c->bigTma = value ? 1 : 0; return AME_OK;
+        case AME_OPT_GROUP_BY_REF: c->groupByRef = value ? 1 : 0; return AME_OK;
     }
     return fail(AME_E_INVALID, "ame_set_option: unknown option %d", option);
 }
@@ -457,7 +462,7 @@ int ame_flush(ame_ctx *c) {
     kp.slotTab = c->dSlotTab; kp.extraIter = c->queuedExtra;
     kp.state = c->dState; kp.accum = c->dAccum; kp.accumStride = (unsigned)c->seqSlots;
     kp.reuseStart = c->reuseStart; kp.shareFirst = c->shareFirst; kp.tab0 = c->dTab0; kp.bigTma = c->bigTma;
-    kp.work = c->dWork; kp.tele = c->dTele; kp.gwOut = c->dGwOut;
+    kp.work = c->dWork; kp.tele = c->dTele; kp.gwOut = c->dGwOut; kp.rowTab = c->dRowTab;
     for (int b = 0; b < 2; b++) {
         kp.smallList[b] = c->dSmallList + (size_t)b * c->seqSlots;
         kp.bigList[b] = c->dBigList + (size_t)b * c->bigCap;
@@ -473,6 +478,21 @@ int ame_flush(ame_ctx *c) {
         kp.passes = c->dPasses + first + k0;
         const size_t words = scan_words((size_t)m * c->nCtus * kSlotsPerCtu);  // the three scan arrays of this sequence, back to back
         kp.scanEmit[0] = c->dScan; kp.scanEmit[1] = c->dScan + words; kp.scanPhase = c->dScan + 2 * words;
+        {   // rows of the state array: passes that search the same reference plane are interleaved CTU by CTU (stable in pass order)
+            std::vector<int> order(m);
+            for (int i = 0; i < m; i++) order[i] = i;
+            if (c->groupByRef) std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return batch[k0 + a].refSlot < batch[k0 + b].refSlot; });
+            std::vector<unsigned> rows((size_t)m * c->nCtus);
+            size_t r = 0;
+            for (int i0 = 0; i0 < m;) {
+                int i1 = i0;
+                while (i1 < m && (c->groupByRef ? batch[k0 + order[i1]].refSlot == batch[k0 + order[i0]].refSlot : i1 == i0)) i1++;
+                for (int ctu = 0; ctu < c->nCtus; ctu++)
+                    for (int i = i0; i < i1; i++) rows[r++] = (unsigned)order[i] | ((unsigned)ctu << 16);
+                i0 = i1;
+            }
+            CU_POISON(cudaMemcpyAsync(c->dRowTab, rows.data(), rows.size() * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));  // (pageable source: staged before the call returns)
+        }
         for (int i = 0; i < m; i++) {
             pt.p[i].curBlk = c->hPasses[first + k0 + i].curBlk;
             pt.p[i].refT = c->hPasses[first + k0 + i].refT;

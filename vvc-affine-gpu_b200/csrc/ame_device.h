@@ -112,7 +112,10 @@ struct KParams {
     int cvtRule, fusedBacksub, earlyExit;
     const PassDesc *passes;   // device array [nPasses]
     const uint32_t *slotTab;  // device array [kSlotsPerCtu]: packed CU word of every slot
-    CuState *state;           // [nPasses * nCtus * kSlotsPerCtu] search state, pass-major
+    const unsigned *rowTab;   // device array [nPasses * nCtus]: pass | ctu << 16 of every row of the state array.  The order of the rows
+                              // is the order of the work lists: passes that search the SAME reference plane are interleaved CTU by
+                              // CTU, so that the warps resident at one time work on one region of one reference plane
+    CuState *state;           // [nPasses * nCtus][kSlotsPerCtu] search state, rows in rowTab order
     CuAccum *accum;           // [2][accumStride], same indexing: SATD and moments of the iteration in flight / of the best state
     unsigned accumStride;
     WorkLists *work;          // [kMaxSteps] sizes and ticket counters of the lists of every step
