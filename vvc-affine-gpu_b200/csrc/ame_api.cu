@@ -76,7 +76,7 @@ struct ame_ctx {
     uint4 *dSmallList = nullptr;              // [2][seqSlots]
     uint2 *dBigList = nullptr;                // [2][bigCap]
     unsigned *dGwOut = nullptr;               // [2 * seqSlots]
-    unsigned *dRowTab = nullptr;              // [seqPasses * nCtus] (pass, CTU) of every row of the state array, per launch sequence
+    unsigned *dRowTab = nullptr;              // [2][seqPasses * nCtus] (pass, CTU) of every row of the state array + the units of ame_iter0_kernel, per launch sequence
     int groupByRef = 1;                       // rows ordered (reference plane, CTU, pass) instead of (pass, CTU)
     size_t bigCap = 0;
     unsigned long long *dScan = nullptr;      // 4 x scan_words(seqSlots): ordered compaction of the update / phase kernels
@@ -257,8 +257,8 @@ int ame_create(ame_ctx **out, int device, int width, int height, int num_slots, 
         }
         c->bigCap = seqPasses * c->nCtus * 9;
         CTX_TRY(cudaMalloc(&c->dGwOut, 2 * nSlots * sizeof(unsigned)));
-        CTX_TRY(cudaMalloc(&c->dRowTab, seqPasses * c->nCtus * sizeof(unsigned)));
-        CTX_TRY(cudaMalloc(&c->dTab0, (size_t)kIter0MaxCtas * c->numSMs * (1024 * 45 + 1024) * sizeof(int)));
+        CTX_TRY(cudaMalloc(&c->dRowTab, 2 * seqPasses * c->nCtus * sizeof(unsigned)));
+        CTX_TRY(cudaMalloc(&c->dTab0, (size_t)kIter0MaxCtas * c->numSMs * kTab0Ints * sizeof(int)));
         CTX_TRY(cudaMalloc(&c->dWork, sizeof(WorkLists) * kMaxSteps));
         CTX_TRY(cudaMalloc(&c->dScan, 3 * scan_words(nSlots) * sizeof(unsigned long long)));
         CTX_TRY(cudaMalloc(&c->dTele, sizeof(Telemetry)));
@@ -482,16 +482,21 @@ int ame_flush(ame_ctx *c) {
             std::vector<int> order(m);
             for (int i = 0; i < m; i++) order[i] = i;
             if (c->groupByRef) std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return batch[k0 + a].refSlot < batch[k0 + b].refSlot; });
-            std::vector<unsigned> rows((size_t)m * c->nCtus);
-            size_t r = 0;
+            const size_t nRows = (size_t)m * c->nCtus;
+            std::vector<unsigned> rows(2 * nRows);  // rows, then the units of ame_iter0_kernel: runs of <= kIter0Unit rows of one (reference plane, CTU)
+            size_t r = 0, u = nRows;
             for (int i0 = 0; i0 < m;) {
                 int i1 = i0;
                 while (i1 < m && (c->groupByRef ? batch[k0 + order[i1]].refSlot == batch[k0 + order[i0]].refSlot : i1 == i0)) i1++;
-                for (int ctu = 0; ctu < c->nCtus; ctu++)
+                for (int ctu = 0; ctu < c->nCtus; ctu++) {
+                    for (int i = i0; i < i1; i += kIter0Unit) rows[u++] = (unsigned)(r + (i - i0)) | ((unsigned)std::min(kIter0Unit, i1 - i) << 24);
                     for (int i = i0; i < i1; i++) rows[r++] = (unsigned)order[i] | ((unsigned)ctu << 16);
+                }
                 i0 = i1;
             }
-            CU_POISON(cudaMemcpyAsync(c->dRowTab, rows.data(), rows.size() * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));  // (pageable source: staged before the call returns)
+            kp.unitTab = c->dRowTab + nRows;
+            kp.nUnits = (int)(u - nRows);
+            CU_POISON(cudaMemcpyAsync(c->dRowTab, rows.data(), u * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));  // (pageable source: staged before the call returns)
         }
         for (int i = 0; i < m; i++) {
             pt.p[i].curBlk = c->hPasses[first + k0 + i].curBlk;

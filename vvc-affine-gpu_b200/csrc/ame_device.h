@@ -104,6 +104,9 @@ struct Telemetry {
 };
 
 constexpr int kIter0MaxCtas = 4;  // resident CTAs per SM ame_iter0_kernel may be built for (AME_ITER0_CTAS)
+// scratch of one CTA of ame_iter0_kernel (ints): [sub-block][case][sum] + [sub-block] SATD + [CU][18] int64 moments shared by the searches of a unit
+constexpr int kTab0Ints = 1024 * 45 + 1024 + (AME_ALIGNED_CUS_PER_CTU + AME_HALF_CUS_PER_CTU) * 18 * 2;
+constexpr int kIter0Unit = 8;     // searches of one (reference plane, CTU) ame_iter0_kernel evaluates in one turn
 
 struct KParams {
     int W, H, ctuCols, nCtus, padStride;
@@ -115,6 +118,9 @@ struct KParams {
     const unsigned *rowTab;   // device array [nPasses * nCtus]: pass | ctu << 16 of every row of the state array.  The order of the rows
                               // is the order of the work lists: passes that search the SAME reference plane are interleaved CTU by
                               // CTU, so that the warps resident at one time work on one region of one reference plane
+    const unsigned *unitTab;  // device array [nUnits]: first row | number of rows << 24 of the runs of up to kIter0Unit rows of rowTab
+                              // that belong to one CTU and one reference plane (ame_iter0_kernel)
+    int nUnits;
     CuState *state;           // [nPasses * nCtus][kSlotsPerCtu] search state, rows in rowTab order
     CuAccum *accum;           // [2][accumStride], same indexing: SATD and moments of the iteration in flight / of the best state
     unsigned accumStride;
@@ -125,7 +131,7 @@ struct KParams {
     unsigned long long *scanEmit[2];  // ordered compaction (decoupled look-back) of ame_emit_kernel: one word per 128-CU chunk, buffer s & 1
     unsigned long long *scanPhase;    // same for ame_phase_kernel
     Telemetry *tele;
-    int *tab0;                // scratch of ame_iter0_kernel: [kIter0MaxCtas * numSMs CTAs][1024 * 45 + 1024]
+    int *tab0;                // scratch of ame_iter0_kernel: [kIter0MaxCtas * numSMs CTAs][kTab0Ints]
     int shareFirst;           // 1: the first evaluation of all 2-CP searches is shared per sub-block (ame_iter0_kernel)
     int reuseStart;           // 1: the 3-CP search reuses the evaluation of the best 2-CP state where the motion fields agree
     int extraIter;            // --ExtraGradientIter of this batch (uniform per launch sequence)
