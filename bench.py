@@ -268,11 +268,15 @@ def size_name(w, h):
 
 # ----------------------------------------------------------------------------- evidence that goes stale with the kernels
 def kernel_source_sha():
+    """Hash of the CUDA sources as code: // comments and white space do not count, every token does."""
+    import re
     hsh = hashlib.sha256()
     d = os.path.join(ROOT, "vvc-affine-gpu_b200", "csrc")
     for name in sorted(os.listdir(d)):
         if name.endswith((".cu", ".h")):
-            hsh.update(open(os.path.join(d, name), "rb").read())
+            text = open(os.path.join(d, name), encoding="utf-8", errors="replace").read()
+            text = re.sub(r"//[^\n]*", "", text)
+            hsh.update(re.sub(r"\s+", "", text).encode())
     return hsh.hexdigest()[:16]
 
 

@@ -460,7 +460,24 @@ def test_error_behaviour(pkg):
             ctx.search(0, 1, 10.0, res)
         ctx.sync()
         assert int(res.cost[0][0]) == int(np.floor(np.float32(10.0) * np.float32(6)))  # zero residual, minimum rate
+        # the calls added in round 2: a slot without a plane cannot be prepared, times need a quiet context
+        with pytest.raises(pkg.AmeError, match="out of range"):
+            ctx.prepare(7, pkg.ROLE_CURRENT)
+        ctx.prepare(1, pkg.ROLE_REFERENCE)
+        ctx.search(0, 1, 10.0, res)
+        with pytest.raises(pkg.AmeError, match="in flight"):
+            ctx.exec_ns()
+        ctx.sync()
+        assert sum(ctx.exec_ns(reset=True)) > 0
+        with pytest.raises(pkg.AmeError, match="extra_iters"):
+            ctx.search(0, 1, 10.0, res, extra_iters=65)
         res.free()
+    finally:
+        ctx.close()
+    ctx = pkg.AffineME(416, 240, num_slots=2, max_in_flight=1)
+    try:
+        with pytest.raises(pkg.AmeError, match="holds no plane"):
+            ctx.prepare(0, pkg.ROLE_CURRENT)
     finally:
         ctx.close()
     with pytest.raises(pkg.AmeError):
