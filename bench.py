@@ -266,6 +266,37 @@ def size_name(w, h):
     return {(1920, 1080): "1080p", (3840, 2160): "4K", (7680, 4320): "8K"}.get((w, h), "%dx%d" % (w, h))
 
 
+# ----------------------------------------------------------------------------- host side of the drop-in CLI
+def host_io_rates(orig2, recon2, qp):
+    """CSV-ingest and log-writer throughput of the drop-in CLI (vvc-affine-gpu_b200/bin/affine_b200) on two frames of the
+    workload: the CLI prints both (CSV_INGEST / LOG_WRITE lines of its timing block).  None if the CLI is not built."""
+    import re
+    import shutil
+    import tempfile
+    cli = os.path.join(ROOT, "vvc-affine-gpu_b200", "bin", "affine_b200")
+    if not os.path.exists(cli):
+        return None
+    tmp = tempfile.mkdtemp(prefix="ame_bench_io_")
+    try:
+        n, h, w = orig2.shape
+        for name, planes in (("o.csv", orig2), ("r.csv", recon2)):
+            with open(os.path.join(tmp, name), "w") as f:
+                for k in range(n):
+                    f.write("\n".join(",".join(map(str, row)) for row in planes[k].tolist()))
+                    f.write("\n")
+        r = subprocess.run([cli, "-f", str(n), "-s", "%dx%d" % (w, h), "-q", str(qp), "-o", os.path.join(tmp, "o.csv"), "-r", os.path.join(tmp, "r.csv"),
+                            "-l", os.path.join(tmp, "log")], capture_output=True, text=True, timeout=300)
+        m1 = re.search(r"^CSV_INGEST,([0-9.]+) MB/s,([0-9.]+) samples/s", r.stdout, re.M)
+        m2 = re.search(r"^LOG_WRITE,([0-9.]+) rows/s", r.stdout, re.M)
+        if r.returncode != 0 or not m1:
+            return {"error": (r.stdout[-300:] + r.stderr[-300:])}
+        return {"csv_ingest_mb_per_s": float(m1.group(1)), "csv_ingest_samples_per_s": float(m1.group(2)),
+                "log_write_rows_per_s": float(m2.group(1)) if m2 else None, "frames": n,
+                "what": "affine_b200 on %d frames of this workload as CSV text (both input files parsed in parallel into pinned planes; 40 log files written)" % n}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 # ----------------------------------------------------------------------------- evidence that goes stale with the kernels
 def kernel_source_sha():
     """Hash of the CUDA sources as code: // comments and white space do not count, every token does."""
@@ -531,6 +562,7 @@ def run_b200(args, rank, world, local_rank):
         if world == 1:
             rows = {"1080p": 9, "4k": 6, "8k": 3, "shard4096": 9}[args.config]
             cb = cpu_port_rate(orig[0], recon[32][0], 32, rows, n_frames / float(n_pass))
+        host_io = host_io_rates(orig[:2], recon[qps[-1]][:2], qps[-1]) if (world == 1 and args.config == "1080p") else None
         line = {
             "metric": "%s frames/sec affine ME" % size_name(w, h), "value": frames_per_s, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -564,6 +596,7 @@ def run_b200(args, rank, world, local_rank):
                                      ops_pass / 1e9, sm_mhz, S * OPS_PER_SAMPLE_FACTORISED / 1e9, algo_bytes, algo_bytes * per_gpu_passes / 1e9,
                                      peaks.get("hbm_gbs", 6650.0)),
                          "kernel_ms_last_sequence": kernel_ms},
+            "host_io": host_io,
             "cpu_baseline": None if cb is None else {
                 "value": cb[0], "unit": "frames/s", "cores": cb[3], "kind": "port",
                 "sample": "CTU rows 0-%d of one %dx%d reference pass (poc 1, ref 0, QP 32), %.1f s, extrapolated by CTU count" % (
