@@ -567,6 +567,16 @@ def test_cli_logs_are_byte_identical_to_the_reference(pkg, tmp_path):
                 got = open(prefix + ame_logs.PRED_TAGS[pred] + nm + ".csv", "rb").read()
                 assert got == _expected_log_bytes(d, W, H, pred, nm), (pred, nm)
 
+    # --RawFrames (extension): the same planes as raw 16-bit samples give the same logs
+    d["orig"].astype("<u2").tofile(str(tmp_path / "orig.raw"))
+    d["recon"].astype("<u2").tofile(str(tmp_path / "recon.raw"))
+    prefix = str(tmp_path / "lograw")
+    r = subprocess.run([pkg.CLI_PATH, "-f", str(n), "-s", "%dx%d" % (W, H), "-q", "32", "-o", str(tmp_path / "orig.raw"), "-r", str(tmp_path / "recon.raw"),
+                        "-l", prefix, "--RawFrames"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for f in ame_logs.log_files(prefix):
+        assert open(f, "rb").read() == open(f.replace("lograw", "log0"), "rb").read(), f
+
 
 REF_ON_LIB = os.path.join(ROOT, "oracle", "_ref", "affine_ref_ame")
 

@@ -25,6 +25,7 @@ struct Options {
     std::string cpmvLogFile;    // -l / --CpmvLogFile (default "": no files)
     int numDevices = 1;         // --NumDevices (extension: shard frames over GPUs DeviceIndex..+N-1)
     int batchFrames = 8;        // --BatchFrames (extension: frames queued per launch)
+    bool rawFrames = false;     // --RawFrames (extension: inputs are raw uint16 planes, not CSV text)
     bool deviceIndexSet = false, logSet = false, qpSet = false, framesSet = false, extraSet = false, resSet = false,
          origSet = false, refSet = false, help = false;
 };
@@ -43,6 +44,8 @@ void print_reference_plan(int nFrames, int inputQp);    // testReferences, main_
 // ---- csv_ingest.cpp: main.cpp:303-328.  Parses nFrames*H lines of W comma-separated samples into dst
 // (nFrames*W*H uint16, e.g. pinned memory).  Returns 0 or -1 (message in err).
 int read_csv_frames(const std::string &path, int nFrames, int W, int H, uint16_t *dst, int threads, std::string &err);
+// Same destination from a file of raw little-endian uint16 samples (nFrames * H * W of them; --RawFrames).
+int read_raw_frames(const std::string &path, int nFrames, int W, int H, uint16_t *dst, std::string &err);
 
 // ---- log_writer.cpp: reportAffineResultsMaster_new, main_aux_functions.h:387-525
 class LogWriter {

@@ -23,6 +23,7 @@ static const OptSpec kOpts[] = {
     {"CpmvLogFile", 'l', true, "Output files preffix with produced CPMVs"},
     {"NumDevices", 0, true, "(extension) shard frames over this many GPUs starting at DeviceIndex"},
     {"BatchFrames", 0, true, "(extension) frames queued per kernel launch"},
+    {"RawFrames", 0, false, "(extension) the two input files hold raw little-endian 16-bit samples (frames stacked) instead of CSV text"},
 };
 
 void print_help() {
@@ -78,6 +79,7 @@ int parse_options(int argc, char **argv, Options &o) {
         else if (n == "CpmvLogFile") { o.cpmvLogFile = val; o.logSet = true; }
         else if (n == "NumDevices") ok = to_int(val, o.numDevices);
         else if (n == "BatchFrames") ok = to_int(val, o.batchFrames);
+        else if (n == "RawFrames") o.rawFrames = true;
         if (!ok) { std::cerr << "the argument ('" << val << "') for option '--" << n << "' is invalid\n"; return 1000 + 1; }
     }
     return 0;

@@ -67,4 +67,14 @@ int read_csv_frames(const std::string &path, int nFrames, int W, int H, uint16_t
     return 0;
 }
 
+int read_raw_frames(const std::string &path, int nFrames, int W, int H, uint16_t *dst, std::string &err) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) { err = "error while opening samples files: " + path; return -1; }
+    const size_t want = (size_t)nFrames * W * H;
+    const size_t got = fread(dst, sizeof(uint16_t), want, f);
+    fclose(f);
+    if (got != want) { err = "file has fewer than FramesToBeEncoded*height*width samples: " + path; return -1; }
+    return 0;
+}
+
 }  // namespace host

@@ -3,7 +3,7 @@
 // include/affine_me.h.  No OpenCL, no CPU fallback.
 //
 // Frame pipeline: both CSV files are parsed into pinned planes; frames are processed in batches of
-// --BatchFrames; batch b runs on GPU (DeviceIndex + b % NumDevices) with its own ame_ctx and host thread
+// --BatchFrames; batch b runs on GPU (DeviceIndex + b % NumDevices), every GPU with its own ame_ctx and host thread
 // (frames are mutually independent given the input files); the log writer consumes batches in
 // POC order, so the logs are byte-identical to the single-GPU order.
 #include <math.h>
@@ -38,8 +38,7 @@ struct Batch {
     std::vector<PassOut> passes;           // in (poc, ref) order
     std::vector<std::pair<int, int>> ids;  // (poc, ref)
     bool done = false;
-    double kernelMs = 0;      // device time of the batch's launch sequence (CUDA events)
-    double execNs[4] = {0, 0, 0, 0};  // the same time per prediction type (ame_exec_ns)
+    double execNs[4] = {0, 0, 0, 0};  // device time of the batch's searches per prediction type (its share of the group's ame_exec_ns)
     double tDone = 0;         // host clock when the results of the batch were complete
     int device = 0;
 };
@@ -113,9 +112,14 @@ int main(int argc, char **argv) {
         std::string e1, e2;
         const int threads = std::max(1u, std::thread::hardware_concurrency());
         int r1 = 0, r2 = 0;
-        std::thread t1([&] { r1 = read_csv_frames(o.origFile, N, W, H, orig, std::max(1, threads / 2), e1); });
-        r2 = read_csv_frames(o.refFile, N, W, H, recon, std::max(1, threads / 2), e2);
-        t1.join();
+        if (o.rawFrames) {
+            r1 = read_raw_frames(o.origFile, N, W, H, orig, e1);
+            r2 = read_raw_frames(o.refFile, N, W, H, recon, e2);
+        } else {
+            std::thread t1([&] { r1 = read_csv_frames(o.origFile, N, W, H, orig, std::max(1, threads / 2), e1); });
+            r2 = read_csv_frames(o.refFile, N, W, H, recon, std::max(1, threads / 2), e2);
+            t1.join();
+        }
         if (r1 || r2) {
             fprintf(stderr, "%s\n", (r1 ? e1 : e2).c_str());
             return 1;
@@ -129,16 +133,39 @@ int main(int argc, char **argv) {
     print_timestamp("FINISH BUILD KERNELS");
 
     // ---- contexts, one per GPU ----
+    // A GPU works on GROUPS of kGroup batches: every batch of a group is uploaded, searched and flushed with its own plane slots,
+    // result blocks and pinned host blocks, then ONE ame_sync waits for the group -- the uploads of a batch and the result
+    // copies of the batch before it run beside the kernels.  All device and pinned memory is allocated here, once (the
+    // reference allocates its buffers in this stage too, main.cpp:330-359, 484-552): pinned allocation and release synchronise
+    // the device, and 250 of each per 64 frames cost seven times the search itself.
     print_timestamp("START ALLOCATE MEMORY");
     const int nDev = std::max(1, o.numDevices);
     // frames per batch: --BatchFrames, but never so many that a GPU is left without a batch
-    const int B = std::max(1, std::min(o.batchFrames, (N + nDev - 1) / nDev));
-    const int slots = 2 * B + 8;  // B current planes + up to B+3 reference planes (+ slack)
-    const int inflight = 4 * B;
+    int B = std::max(1, std::min(o.batchFrames, (N + nDev - 1) / nDev));
+    // Reference slots dominate the device memory (2 x 16 pre-filtered planes each: 0.2 GB at 1080p, 2.6 GB at 8K): batches per
+    // group, then frames per batch, are cut back until they fit a budget of 64 GB.
+    const double slotBytes = 32.0 * (W + 320.0) * (H + 320.0) * 2.0, budget = 64e9;
+    while (B > 1 && (B + 8) * slotBytes > budget) B--;
+    const int kGroup = (int)std::max(1.0, std::min(4.0, budget / ((B + 8) * slotBytes)));
+    const int slotsPerBatch = 2 * B + 8;  // B current planes + up to B+3 reference planes (+ slack)
+    const int passesPerBatch = 4 * B;
     std::vector<ame_ctx *> ctxs(nDev, nullptr);
+    std::vector<std::vector<PassOut>> pool(nDev);  // [device][2 sets x kGroup batches x passesPerBatch]
     for (int d = 0; d < nDev; d++) {
-        if (ame_create(&ctxs[d], o.deviceIndex + d, W, H, slots, inflight) != AME_OK) {
+        if (ame_create(&ctxs[d], o.deviceIndex + d, W, H, kGroup * slotsPerBatch, kGroup * passesPerBatch) != AME_OK) {
             fprintf(stderr, "ame_create(device %d) failed: %s\n", o.deviceIndex + d, ame_last_error());
+            return 1;
+        }
+        bool ok = true;
+        for (int s = 0; ok && s < kGroup * slotsPerBatch; s++)  // the device-side copies of every slot, in the role it will have
+            ok = ame_upload_plane_ex(ctxs[d], s, s % slotsPerBatch < B ? orig : recon, s % slotsPerBatch < B ? AME_ROLE_CURRENT : AME_ROLE_REFERENCE) == AME_OK;
+        ok = ok && ame_sync(ctxs[d]) == AME_OK;
+        pool[d].resize((size_t)2 * kGroup * passesPerBatch);
+        for (PassOut &p : pool[d]) ok = ok && alloc_pass(p, ctxs[d]);
+        double dummy[4];
+        ok = ok && ame_exec_ns(ctxs[d], dummy, 1) == AME_OK;
+        if (!ok) {
+            fprintf(stderr, "allocation on device %d failed: %s\n", o.deviceIndex + d, ame_last_error());
             return 1;
         }
     }
@@ -158,52 +185,74 @@ int main(int argc, char **argv) {
     std::condition_variable cv;
     int written = 0;  // batches consumed by the writer
     bool failed = false;
-    const int kAhead = 2 * nDev;  // a GPU may run at most this many batches ahead of the writer (bounds pinned memory)
 
     print_timestamp("START GPU KERNEL");
     const double t0 = now_s();
 
     auto worker = [&](int d) {
         ame_ctx *ctx = ctxs[d];
-        for (int b = d; b < nBatches; b += nDev) {
-            {
+        // batches of this GPU: d, d + nDev, ...; group gi = kGroup consecutive ones of them, pinned set gi & 1
+        for (int gi = 0;; gi++) {
+            std::vector<int> mine;
+            for (int j = 0; j < kGroup; j++) {
+                const int b = d + nDev * (gi * kGroup + j);
+                if (b < nBatches) mine.push_back(b);
+            }
+            if (mine.empty()) return;
+            {   // the pinned set was last used by group gi - 2: the writer must be through with it
+                const int lastOld = d + nDev * ((gi - 2) * kGroup + kGroup - 1);
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return failed || b < written + kAhead; });
+                cv.wait(lk, [&] { return failed || gi < 2 || written > std::min(lastOld, nBatches - 1); });
                 if (failed) return;
             }
-            Batch &bt = batches[b];
-            bt.passes.resize(bt.ids.size());
             bool ok = true;
-            bt.device = o.deviceIndex + d;
-            for (PassOut &p : bt.passes) ok = ok && alloc_pass(p, ctx);
-            // planes: slot i < B holds current frame firstFrame+i; reference POCs get the following slots
-            std::map<int, int> refSlot;
-            for (int i = 0; ok && i < bt.nFrames; i++) {
-                const int f = bt.firstFrame + i;
-                ok = ok && ame_upload_plane_ex(ctx, i, orig + plane * f, AME_ROLE_CURRENT) == AME_OK;
-                for (int rp : lists[f]) {
-                    if (refSlot.count(rp)) continue;
-                    const int s = B + (int)refSlot.size();
-                    refSlot[rp] = s;
-                    ok = ok && ame_upload_plane_ex(ctx, s, recon + plane * rp, AME_ROLE_REFERENCE) == AME_OK;
+            size_t groupPasses = 0;
+            for (size_t j = 0; ok && j < mine.size(); j++) {
+                Batch &bt = batches[mine[j]];
+                bt.device = o.deviceIndex + d;
+                bt.passes.resize(bt.ids.size());
+                const size_t poolBase = ((size_t)(gi & 1) * kGroup + j) * passesPerBatch;
+                for (size_t k = 0; k < bt.ids.size(); k++) bt.passes[k] = pool[d][poolBase + k];
+                // planes: slot i < B of the batch's slot set holds current frame firstFrame+i; reference POCs get the following slots
+                const int slot0 = (int)j * slotsPerBatch;
+                std::map<int, int> refSlot;
+                for (int i = 0; ok && i < bt.nFrames; i++) {
+                    const int f = bt.firstFrame + i;
+                    ok = ok && ame_upload_plane_ex(ctx, slot0 + i, orig + plane * f, AME_ROLE_CURRENT) == AME_OK;
+                    for (int rp : lists[f]) {
+                        if (refSlot.count(rp)) continue;
+                        const int s = slot0 + B + (int)refSlot.size();
+                        refSlot[rp] = s;
+                        ok = ok && ame_upload_plane_ex(ctx, s, recon + plane * rp, AME_ROLE_REFERENCE) == AME_OK;
+                    }
                 }
-            }
-            for (size_t k = 0; ok && k < bt.ids.size(); k++) {
-                const int poc = bt.ids[k].first, r = bt.ids[k].second, f = poc - 1;
-                ok = ok && ame_search(ctx, f - bt.firstFrame, refSlot[lists[f][r]], lambda_for(o.qp, poc), o.extraGradIter, &bt.passes[k].res) == AME_OK;
+                for (size_t k = 0; ok && k < bt.ids.size(); k++) {
+                    const int poc = bt.ids[k].first, r = bt.ids[k].second, f = poc - 1;
+                    ok = ok && ame_search(ctx, slot0 + f - bt.firstFrame, refSlot[lists[f][r]], lambda_for(o.qp, poc), o.extraGradIter, &bt.passes[k].res) == AME_OK;
+                }
+                ok = ok && ame_flush(ctx) == AME_OK;
+                groupPasses += bt.ids.size();
             }
             ok = ok && ame_sync(ctx) == AME_OK;
-            float ms = 0;
-            int nl = 0;
-            if (ok && ame_last_kernel_ms(ctx, &ms, &nl) == AME_OK) bt.kernelMs = ms;
-            ok = ok && ame_exec_ns(ctx, bt.execNs, 1) == AME_OK;
-            bt.tDone = now_s();
+            double ns[4] = {0, 0, 0, 0};
+            ok = ok && ame_exec_ns(ctx, ns, 1) == AME_OK;
+            const double tDone = now_s();
             std::lock_guard<std::mutex> lk(mu);
             if (!ok) {
                 fprintf(stderr, "GPU %d: %s\n", o.deviceIndex + d, ame_last_error());
                 failed = true;
             }
-            bt.done = true;
+            // the device times of the group go to its batches by their share of the passes, laid out back to back before tDone
+            double tail = 0;
+            for (size_t j = mine.size(); j-- > 0;) {
+                Batch &bt = batches[mine[j]];
+                const double share = groupPasses ? (double)bt.ids.size() / (double)groupPasses : 0.0;
+                double batchNs = 0;
+                for (int k = 0; k < 4; k++) { bt.execNs[k] = ns[k] * share; batchNs += bt.execNs[k]; }
+                bt.tDone = tDone - tail;
+                tail += batchNs * 1e-9;
+                bt.done = true;
+            }
             cv.notify_all();
         }
     };
@@ -212,7 +261,7 @@ int main(int argc, char **argv) {
 
     // ---- writer: consumes batches in POC order (main.cpp:746-748, 980-1003) ----
     LogWriter log(o.cpmvLogFile, W, H);
-    double kernelMs = 0, execNs[4] = {0, 0, 0, 0}, logSeconds = 0;
+    double execNs[4] = {0, 0, 0, 0}, logSeconds = 0;
     std::vector<double> devNs(nDev, 0.0);
     size_t logRows = 0;
     static const char *kExecName[4] = {"FULL 2 CPs", "FULL 3 CPs", "HALF 2 CPs", "HALF 3 CPs"};
@@ -223,7 +272,6 @@ int main(int argc, char **argv) {
             if (failed) break;
         }
         Batch &bt = batches[b];
-        kernelMs += bt.kernelMs;
         double batchNs = 0;
         for (int k = 0; k < 4; k++) { execNs[k] += bt.execNs[k]; batchNs += bt.execNs[k]; }
         devNs[bt.device - o.deviceIndex] += batchNs;
@@ -245,8 +293,6 @@ int main(int argc, char **argv) {
             const double tw = now_s();
             logRows += log.write_pass(bt.ids[k].first, bt.ids[k].second, bt.passes[k].res);
             logSeconds += now_s() - tw;
-            ame_free_host(bt.passes[k].block);
-            bt.passes[k].block = nullptr;
         }
         std::lock_guard<std::mutex> lk(mu);
         written = b + 1;
@@ -268,12 +314,13 @@ int main(int argc, char **argv) {
     printf("HALF_3CP_EXEC,%f\n", execNs[3]);
     printf("TOTAL_EXEC_TIME(%dx),%f\n", N, execNs[0] + execNs[1] + execNs[2] + execNs[3]);
     printf("OVERALL(%dx),%f\n", N, overall);
-    printf("LAUNCH_SEQUENCES_EVENT_TIME,%f\n", kernelMs * 1e6);
     for (int d = 0; d < nDev; d++) printf("GPU%d_EXEC,%f\n", o.deviceIndex + d, devNs[d]);
     printf("CSV_INGEST,%.1f MB/s,%.0f samples/s\n", readSeconds > 0 ? csvBytes / readSeconds / 1e6 : 0.0, readSeconds > 0 ? 2.0 * plane * N / readSeconds : 0.0);
     if (log.enabled()) printf("LOG_WRITE,%.0f rows/s\n", logSeconds > 0 ? logRows / logSeconds : 0.0);
     printf("=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=\n\n");
 
+    for (auto &v : pool)
+        for (PassOut &p : v) ame_free_host(p.block);
     for (ame_ctx *c : ctxs) ame_destroy(c);
     ame_free_host(orig);
     ame_free_host(recon);
