@@ -151,7 +151,9 @@ def make_sequences(w=None, h=None, n_frames=None, qps=QPS):
     import multiprocessing as mp
     import synth_frames as sf
     w, h, n_frames = w or W, h or H, n_frames or N_FRAMES
-    with mp.get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:
+    # (one pool per rank: the ranks of a multi-GPU run share the host cores)
+    world = max(1, int(os.environ.get("WORLD_SIZE", "1")))
+    with mp.get_context("fork").Pool(max(2, min(16, host_cores() // world))) as pool:
         frames = pool.map(_gen_frame, [(t, w, h) for t in range(n_frames + 1)])
     frames = np.stack(frames)
     recon = {}
